@@ -1,0 +1,122 @@
+// Python bindings of the sm_100a kernels.  Ops are thin objects that own a filled launch
+// struct (raw device addresses supplied by Python, which keeps the tensors alive) and launch on
+// PyTorch's current CUDA stream, so they compose with torch.cuda.graph capture: a whole
+// consensus round is captured once and replayed.
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <pybind11/pybind11.h>
+
+#include "consensus.h"
+#include "mnist.h"
+
+namespace py = pybind11;
+using namespace nndt;
+
+static inline cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+static inline void check(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+template <typename P> static P* ptr(const py::dict& d, const char* k) {
+  if (!d.contains(k) || d[k].is_none()) return nullptr;
+  return reinterpret_cast<P*>(d[k].cast<uint64_t>());
+}
+static int geti(const py::dict& d, const char* k, int dflt = 0) { return d.contains(k) ? d[k].cast<int>() : dflt; }
+static double getf(const py::dict& d, const char* k, double dflt = 0) { return d.contains(k) ? d[k].cast<double>() : dflt; }
+
+// ------------------------------------------------------------------ MNIST ----
+struct MnistOp {
+  mnist::Args a{};
+  int spb = 8, S = 1, eval_ctas = 1;
+  explicit MnistOp(const py::dict& d) { update(d); }
+  void update(const py::dict& d) {
+    a.theta = ptr<const float>(d, "theta"); a.n_pad = geti(d, "n_pad"); a.L = geti(d, "L");
+    a.off_wc = geti(d, "off_wc"); a.off_bc = geti(d, "off_bc"); a.off_w1 = geti(d, "off_w1");
+    a.off_b1 = geti(d, "off_b1"); a.off_w2 = geti(d, "off_w2"); a.off_b2 = geti(d, "off_b2");
+    a.x = ptr<const void>(d, "x"); a.y = ptr<const int64_t>(d, "y");
+    a.x_is_u8 = geti(d, "x_is_u8"); a.mean = (float)getf(d, "mean"); a.inv_std = (float)getf(d, "inv_std", 1.0);
+    a.direct = geti(d, "direct"); a.batch = geti(d, "batch"); a.seed = geti(d, "seed"); a.node0 = geti(d, "node0");
+    a.shard_off = ptr<const int>(d, "shard_off"); a.shard_len = ptr<const int>(d, "shard_len");
+    a.calls = ptr<const int>(d, "calls");
+    a.grad_part = ptr<float>(d, "grad_part"); a.loss_part = ptr<float>(d, "loss_part");
+    a.n_val = geti(d, "n_val"); a.val_loss = ptr<float>(d, "val_loss");
+    a.val_correct = ptr<unsigned char>(d, "val_correct");
+    spb = geti(d, "spb", 8); S = geti(d, "S", 1); eval_ctas = geti(d, "eval_ctas", 1);
+  }
+  void train() { check(mnist::launch_train(a, spb, S, cur_stream()), "mnist_train"); }
+  void eval() { check(mnist::launch_eval(a, eval_ctas, cur_stream()), "mnist_eval"); }
+};
+
+// -------------------------------------------------------------- consensus ----
+template <typename T>
+static consensus::Common<T> common_from(const py::dict& d) {
+  consensus::Common<T> c{};
+  c.L = geti(d, "L"); c.n_pad = geti(d, "n_pad"); c.S = geti(d, "S", 1);
+  c.theta = ptr<T>(d, "theta"); c.grad_part = ptr<const T>(d, "grad_part");
+  c.pub = ptr<T>(d, "pub"); c.C = geti(d, "C", 1); c.pub_L = geti(d, "pub_L", c.L);
+  c.nbr_ptr = ptr<const int64_t>(d, "nbr_ptr"); c.nbr_w = ptr<const T>(d, "nbr_w");
+  c.self_w = ptr<const T>(d, "self_w"); c.deg = ptr<const int>(d, "deg");
+  c.nbr_rank = ptr<const int>(d, "nbr_rank"); c.dmax = geti(d, "dmax");
+  c.round_ctr = ptr<int>(d, "round_ctr");
+  c.rho = ptr<const T>(d, "rho"); c.lr = ptr<const T>(d, "lr"); c.alpha = ptr<const T>(d, "alpha");
+  c.graph_id = ptr<const int>(d, "graph_id");
+  c.calls = ptr<int>(d, "calls");
+  c.flags = ptr<int>(d, "flags"); c.peer_flag = ptr<const int64_t>(d, "peer_flag");
+  c.world = geti(d, "world", 1); c.rank = geti(d, "rank", 0);
+  c.done_ctr = ptr<unsigned int>(d, "done_ctr"); c.err = ptr<int>(d, "err");
+  return c;
+}
+
+template <typename T>
+struct ConsensusOp {
+  consensus::Common<T> c{};
+  consensus::DinnoArgs<T> dn{};
+  consensus::DsgtArgs<T> gt{};
+  explicit ConsensusOp(const py::dict& d) {
+    c = common_from<T>(d);
+    dn.c = c; gt.c = c;
+    dn.dual = ptr<T>(d, "dual"); dn.delta = ptr<T>(d, "delta"); dn.m = ptr<T>(d, "m"); dn.v = ptr<T>(d, "v");
+    dn.pits = geti(d, "pits", 1); dn.opt = geti(d, "opt", 1); dn.persistent = geti(d, "persistent", 0);
+    gt.g_old = ptr<T>(d, "g_old");
+  }
+  void dinno_update(int step) {
+    dn.step = step;
+    check(consensus::launch_dinno_update<T>(dn, cur_stream()), "dinno_update");
+  }
+  void dsgd_mix() { check(consensus::launch_dsgd_mix<T>(c, cur_stream()), "dsgd_mix"); }
+  void dsgd_step() { check(consensus::launch_dsgd_step<T>(c, cur_stream()), "dsgd_step"); }
+  void dsgt_init() { check(consensus::launch_dsgt_init<T>(gt, cur_stream()), "dsgt_init"); }
+  void dsgt_mix() { check(consensus::launch_dsgt_mix<T>(gt, cur_stream()), "dsgt_mix"); }
+  void dsgt_track() { check(consensus::launch_dsgt_track<T>(gt, cur_stream()), "dsgt_track"); }
+};
+
+template <typename T>
+static void bind_consensus(py::module& m, const char* name) {
+  py::class_<ConsensusOp<T>>(m, name)
+      .def(py::init<const py::dict&>())
+      .def("dinno_update", &ConsensusOp<T>::dinno_update)
+      .def("dsgd_mix", &ConsensusOp<T>::dsgd_mix)
+      .def("dsgd_step", &ConsensusOp<T>::dsgd_step)
+      .def("dsgt_init", &ConsensusOp<T>::dsgt_init)
+      .def("dsgt_mix", &ConsensusOp<T>::dsgt_mix)
+      .def("dsgt_track", &ConsensusOp<T>::dsgt_track);
+}
+
+void bind_mlp(py::module& m);     // mlp_bind.cpp
+void bind_runtime(py::module& m); // runtime.cpp
+
+PYBIND11_MODULE(_C, m) {
+  m.doc() = "nn_distributed_training_b200 sm_100a kernels";
+  py::class_<MnistOp>(m, "MnistOp")
+      .def(py::init<const py::dict&>())
+      .def("update", &MnistOp::update)
+      .def("train", &MnistOp::train)
+      .def("eval", &MnistOp::eval);
+  m.def("debug_batch_indices", [](int mm, int B, int call, int seed, int node, uint64_t out, uint64_t out_size) {
+    check(mnist::launch_batch_indices(mm, B, call, seed, node, reinterpret_cast<int*>(out),
+                                      reinterpret_cast<int*>(out_size), cur_stream()), "batch_indices");
+  });
+  bind_consensus<float>(m, "ConsensusOpF32");
+  bind_consensus<double>(m, "ConsensusOpF64");
+  bind_mlp(m);
+  bind_runtime(m);
+}

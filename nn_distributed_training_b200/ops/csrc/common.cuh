@@ -1,0 +1,61 @@
+// Shared device helpers for the sm_100a kernels of nn_distributed_training_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define NNDT_DEVINL __device__ __forceinline__
+
+namespace nndt {
+
+constexpr int kWarp = 32;
+
+NNDT_DEVINL float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+NNDT_DEVINL double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- system-scope flags for cross-GPU producer/consumer sync -----------------
+// A rank publishes round k by (1) writing its rows, (2) __threadfence_system(),
+// (3) st.release.sys of k into the *reader's* flag slot (remote store over NVLink),
+// so readers spin on local memory only.
+NNDT_DEVINL void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+NNDT_DEVINL int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+NNDT_DEVINL int ld_relaxed_sys(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// streaming 128-bit load that bypasses L1 allocation (peer / read-once data)
+NNDT_DEVINL float4 ld_stream_f4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// cp.async helpers (LDGSTS)
+NNDT_DEVINL void cp_async16(void* smem, const void* gmem) {
+  uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+NNDT_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+NNDT_DEVINL void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+}  // namespace nndt

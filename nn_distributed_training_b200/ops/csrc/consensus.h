@@ -1,0 +1,69 @@
+// Launch interface of the fused consensus kernels (consensus.cu).
+//
+// One launch covers every graph node hosted by this GPU.  Neighbor rows are read through a
+// device pointer table, so a neighbor may be another row of the local arena (virtual nodes on
+// one GPU) or a row of a peer GPU's symmetric-memory arena mapped over NVLink — the kernel is
+// identical, the graph only changes which pointers are in the table.  All per-round scalars
+// (rho_k, lr_k, alpha_k, graph id) are indexed by a device-side round counter so a captured
+// CUDA graph can be replayed for any number of rounds with no host involvement.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nndt {
+namespace consensus {
+
+enum Opt : int { kSGD = 0, kAdam = 1, kAdamW = 2 };
+
+template <typename T>
+struct Common {
+  // geometry
+  int L, n_pad, S;            // local nodes, padded row length, gradient partials per node
+  // live state (rows of the local arena)
+  T* theta;                   // [L, n_pad]
+  const T* grad_part;         // [L, S, n_pad]
+  T* pub;                     // [2 parity, C chan, pub_L, n_pad] published rows (symmetric memory)
+  int C, pub_L;
+  // topology tables for G graphs
+  const int64_t* nbr_ptr;     // [G, L, dmax, 2, C] device addresses of neighbor rows per parity/chan
+  const T* nbr_w;             // [G, L, dmax]
+  const T* self_w;            // [G, L]
+  const int* deg;             // [G, L]
+  const int* nbr_rank;        // [G, L, dmax] owning rank of each neighbor, -1 when local
+  int dmax;
+  // device-side schedules
+  int* round_ctr;             // [1]
+  const T* rho; const T* lr; const T* alpha;   // [oits]
+  const int* graph_id;        // [oits]
+  // sampler bookkeeping
+  int* calls;                 // [L] or nullptr
+  // cross-GPU sync (nullptr / 0 when single GPU)
+  int* flags;                 // [world] local slots written by peers (round published)
+  const int64_t* peer_flag;   // [world] address of *their* slot for this rank
+  int world, rank;
+  unsigned int* done_ctr;     // [1] last-block detection
+  int* err;                   // [1] set on spin timeout
+};
+
+template <typename T>
+struct DinnoArgs {
+  Common<T> c;
+  T* dual; T* delta; T* m; T* v;   // [L, n_pad]
+  int step, pits, opt, persistent;
+};
+
+template <typename T>
+struct DsgtArgs {
+  Common<T> c;
+  T* g_old;                        // [L, n_pad]
+};
+
+template <typename T> cudaError_t launch_dinno_update(const DinnoArgs<T>& a, cudaStream_t st);
+template <typename T> cudaError_t launch_dsgd_mix(const Common<T>& c, cudaStream_t st);
+template <typename T> cudaError_t launch_dsgd_step(const Common<T>& c, cudaStream_t st);
+template <typename T> cudaError_t launch_dsgt_init(const DsgtArgs<T>& a, cudaStream_t st);
+template <typename T> cudaError_t launch_dsgt_mix(const DsgtArgs<T>& a, cudaStream_t st);
+template <typename T> cudaError_t launch_dsgt_track(const DsgtArgs<T>& a, cudaStream_t st);
+
+}  // namespace consensus
+}  // namespace nndt

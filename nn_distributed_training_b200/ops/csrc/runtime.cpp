@@ -1,0 +1,3 @@
+#include <pybind11/pybind11.h>
+namespace py = pybind11;
+void bind_runtime(py::module& m) { (void)m; }

@@ -1,0 +1,140 @@
+"""Consensus engine: device tables + fused kernel ops for one optimizer run.
+
+Built once per ``train()``; afterwards a communication round is a fixed sequence
+of kernel launches that reads every per-round scalar from device memory, so the
+sequence is captured in a CUDA graph and replayed (``round_program.py``).
+"""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import numpy as np
+import torch
+
+from . import load_ext
+from ..parallel.symm import SymmetricBuffer
+from ..utils.graph_generation import Topology
+
+OPT_CODE = {"sgd": 0, "adam": 1, "adamw": 2}
+
+
+class ConsensusEngine:
+    def __init__(self, opt, graphs_per_round: List):
+        self.opt = opt
+        pr = self.pr = opt.pr
+        self.ext = load_ext(required=True)
+        dev, a, pl, ctx = pr.device, pr.arena, pr.placement, pr.ctx
+        self.dtype = a.dtype
+        npdt = np.float32 if self.dtype == torch.float32 else np.float64
+        self.C = 2 if opt.alg_name == "dsgt" else 1
+        L, n_pad, oits = pl.L, a.n_pad, opt.oits
+
+        # ---- published rows (double buffered, peer mapped when multi-GPU) -----
+        Lmax = max(pl.counts)
+        self.pub_buf = SymmetricBuffer((2, self.C, Lmax, n_pad), self.dtype, ctx)
+        self.pub = self.pub_buf.local
+        self.Lpub = Lmax
+        self.pub[0, 0, :L].copy_(a.theta)
+
+        # ---- schedules ----------------------------------------------------------
+        k0 = opt.k
+        rho = np.zeros(oits); lr = np.zeros(oits); alpha = np.zeros(oits)
+        if opt.alg_name == "dinno":
+            rho[:] = [opt.rho_at(k) for k in range(oits)]
+            lr[:] = [opt.lr_at(k) for k in range(oits)]
+        elif opt.alg_name == "dsgd":
+            alpha[:] = opt.alpha_table()
+        else:
+            alpha[:] = opt.alpha
+        self.rho = torch.as_tensor(rho.astype(npdt), device=dev)
+        self.lr = torch.as_tensor(lr.astype(npdt), device=dev)
+        self.alpha = torch.as_tensor(alpha.astype(npdt), device=dev)
+
+        # ---- topology tables ------------------------------------------------------
+        topos: List[Topology] = []
+        key_to_id: Dict[bytes, int] = {}
+        gid = np.zeros(oits, dtype=np.int32)
+        for k, g in enumerate(graphs_per_round):
+            t = pr._topo_cache.get(g) if hasattr(pr, "_topo_cache") else Topology(g)
+            if t.key not in key_to_id:
+                key_to_id[t.key] = len(topos)
+                topos.append(t)
+            gid[k] = key_to_id[t.key]
+        self.topos = topos
+        G = len(topos)
+        dmax = max(1, max(t.max_degree for t in topos))
+        itemsize = a.theta.element_size()
+        nbr_ptr = np.zeros((G, L, dmax, 2, self.C), dtype=np.int64)
+        nbr_w = np.zeros((G, L, dmax), dtype=npdt)
+        self_w = np.zeros((G, L), dtype=npdt)
+        deg = np.zeros((G, L), dtype=np.int32)
+        nbr_rank = -np.ones((G, L, dmax), dtype=np.int32)
+        for gi, t in enumerate(topos):
+            for l, g in enumerate(pl.local_nodes):
+                nb = t.neighbors_noself[g]
+                deg[gi, l] = len(nb)
+                self_w[gi, l] = t.W[g, g]
+                for e, j in enumerate(nb):
+                    r, lj = int(pl.node_rank[j]), int(pl.node_local[j])
+                    nbr_w[gi, l, e] = t.W[g, j]
+                    if r != ctx.rank:
+                        nbr_rank[gi, l, e] = r
+                    for par in range(2):
+                        for ch in range(self.C):
+                            row = ((par * self.C + ch) * self.Lpub + lj) * n_pad
+                            nbr_ptr[gi, l, e, par, ch] = self.pub_buf.peer_ptrs[r] + row * itemsize
+        self.dmax = dmax
+        self.t_nbr_ptr = torch.as_tensor(nbr_ptr, device=dev)
+        self.t_nbr_w = torch.as_tensor(nbr_w, device=dev)
+        self.t_self_w = torch.as_tensor(self_w, device=dev)
+        self.t_deg = torch.as_tensor(deg, device=dev)
+        self.t_nbr_rank = torch.as_tensor(nbr_rank, device=dev)
+        self.t_gid = torch.as_tensor(gid, device=dev)
+
+        # ---- counters / flags -----------------------------------------------------
+        self.round_ctr = torch.full((1,), k0, dtype=torch.int32, device=dev)
+        self.done_ctr = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.flag_buf = SymmetricBuffer((max(ctx.world_size, 1),), torch.int32, ctx)
+        self.flag_buf.local.fill_(k0)
+        peer_flag = np.zeros(max(ctx.world_size, 1), dtype=np.int64)
+        for r in range(ctx.world_size):
+            peer_flag[r] = self.flag_buf.peer_ptrs[r] + 4 * ctx.rank
+        self.t_peer_flag = torch.as_tensor(peer_flag, device=dev)
+        if ctx.is_distributed:
+            torch.cuda.synchronize(dev)
+            ctx.barrier()
+
+        # ---- gradient source --------------------------------------------------------
+        if pr.fused is not None:
+            grad_part, S, calls = pr.fused.grad_part, pr.fused.S, pr.fused.calls
+        else:
+            grad_part, S, calls = a.grad, 1, None
+        self.S = S
+
+        d = dict(L=L, n_pad=n_pad, S=S, theta=a.theta.data_ptr(), grad_part=grad_part.data_ptr(),
+                 pub=self.pub.data_ptr(), C=self.C, nbr_ptr=self.t_nbr_ptr.data_ptr(),
+                 nbr_w=self.t_nbr_w.data_ptr(), self_w=self.t_self_w.data_ptr(), deg=self.t_deg.data_ptr(),
+                 nbr_rank=self.t_nbr_rank.data_ptr(), dmax=dmax, round_ctr=self.round_ctr.data_ptr(),
+                 rho=self.rho.data_ptr(), lr=self.lr.data_ptr(), alpha=self.alpha.data_ptr(),
+                 graph_id=self.t_gid.data_ptr(), calls=None if calls is None else calls.data_ptr(),
+                 flags=self.flag_buf.local.data_ptr(), peer_flag=self.t_peer_flag.data_ptr(),
+                 world=ctx.world_size, rank=ctx.rank, done_ctr=self.done_ctr.data_ptr(), err=self.err.data_ptr())
+        # the C++ side indexes pub rows with stride L; when ranks host different node counts the
+        # published buffer is allocated with the max count, so pass that as the row count of pub
+        d["L"] = L
+        d["pub_L"] = self.Lpub
+        if opt.alg_name == "dinno":
+            d.update(dual=opt.duals.data_ptr(), delta=opt.delta.data_ptr(),
+                     m=None if opt.m is None else opt.m.data_ptr(),
+                     v=None if opt.v is None else opt.v.data_ptr(),
+                     pits=opt.pits, opt=OPT_CODE[opt.opt_kind], persistent=int(opt.persistent))
+        if opt.alg_name == "dsgt":
+            d.update(g_old=opt.g.data_ptr())
+        cls = self.ext.ConsensusOpF32 if self.dtype == torch.float32 else self.ext.ConsensusOpF64
+        self.op = cls(d)
+        self._keep = d
+
+    def check(self):
+        if int(self.err.item()) != 0:
+            raise RuntimeError("consensus kernel timed out waiting for a peer's published round")

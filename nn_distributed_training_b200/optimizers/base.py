@@ -117,11 +117,10 @@ class ConsensusOptimizer:
 
     # -- template ----------------------------------------------------------
     def train(self, profiler=None):
-        self._before_training()
-        fused = self.pr.fused is not None and self.mixing_order == "jacobi"
-        if fused:
+        if self._use_engine():
             self._train_fused(profiler)
         else:
+            self._before_training()
             while self.k < self.oits:
                 k = self.k
                 self._maybe_eval(k)
@@ -135,6 +134,19 @@ class ConsensusOptimizer:
 
     def _before_training(self):
         pass
+
+    def _use_engine(self) -> bool:
+        """Fused sm_100a consensus kernels: any arena problem on a CUDA device with the
+        synchronous (Jacobi) update order; the PyTorch ops remain for CPU/gloo, for
+        foreign problem objects and for the reference-order oracle mode."""
+        if self.mixing_order != "jacobi" or not isinstance(self.pr, ConsensusProblem):
+            return False
+        if self.device.type != "cuda" or self.conf.get("consensus_backend", "auto") == "torch":
+            return False
+        if self.arena.dtype not in (torch.float32, torch.float64):
+            return False
+        from ..ops import fused_available
+        return fused_available()
 
     def _round(self, k: int):
         raise NotImplementedError

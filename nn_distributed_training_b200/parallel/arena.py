@@ -15,7 +15,8 @@ from typing import Dict, List, Sequence, Tuple
 import torch
 from torch import nn
 
-ROW_ALIGN_ELEMS = 128  # 512 B for fp32: every row / tensor-independent float4 access is aligned
+ROW_ALIGN_ELEMS = 128  # rows are 512 B aligned (fp32)
+SLOT_ALIGN_ELEMS = 4    # every parameter tensor starts on a 16 B boundary -> float4 / cp.async.16 everywhere
 
 
 @dataclass(frozen=True)
@@ -32,14 +33,16 @@ class FlatLayout:
     def __init__(self, slots: Sequence[ParamSlot]):
         self.slots = list(slots)
         self.n = sum(s.numel for s in self.slots)
-        self.n_pad = ((self.n + ROW_ALIGN_ELEMS - 1) // ROW_ALIGN_ELEMS) * ROW_ALIGN_ELEMS
+        end = max((s.offset + s.numel for s in self.slots), default=0)
+        self.n_pad = ((end + ROW_ALIGN_ELEMS - 1) // ROW_ALIGN_ELEMS) * ROW_ALIGN_ELEMS
+        self.dense = all(a.offset + a.numel == b.offset for a, b in zip(self.slots, self.slots[1:]))
 
     @classmethod
     def from_module(cls, module: nn.Module) -> "FlatLayout":
         slots, off = [], 0
         for name, p in module.named_parameters():
             slots.append(ParamSlot(name, tuple(p.shape), off, p.numel()))
-            off += p.numel()
+            off += -(-p.numel() // SLOT_ALIGN_ELEMS) * SLOT_ALIGN_ELEMS
         return cls(slots)
 
     def offsets(self) -> List[int]:
@@ -52,6 +55,15 @@ class FlatLayout:
 
     def views(self, row: torch.Tensor) -> List[torch.Tensor]:
         return [row[s.offset: s.offset + s.numel].view(s.shape) for s in self.slots]
+
+    def compact(self, t: torch.Tensor) -> torch.Tensor:
+        """``[..., n_pad] -> [..., n]``: drop alignment holes, giving exactly
+        ``parameters_to_vector`` order.  Holes hold zeros forever (every update is
+        elementwise with zero gradient there), so norms/distances may also be
+        taken on padded rows directly."""
+        if self.dense:
+            return t[..., : self.n]
+        return torch.cat([t[..., s.offset: s.offset + s.numel] for s in self.slots], dim=-1)
 
 
 class NodeArena:
@@ -86,6 +98,5 @@ class NodeArena:
         for s, t in zip(self.layout.slots, grads):
             g[s.offset: s.offset + s.numel].copy_(t.reshape(-1))
 
-    def valid(self, t: torch.Tensor) -> torch.Tensor:
-        """Trim the alignment padding: ``[..., n_pad] -> [..., n]``."""
-        return t[..., : self.n]
+    def compact(self, t: torch.Tensor) -> torch.Tensor:
+        return self.layout.compact(t)

@@ -132,6 +132,19 @@ class ConsensusProblem:
             # node 0 is the forward-pass odometer (dist_mnist_problem.py:90-94)
             self.forward_cnt += times * self.train_batch_size
 
+    def count_draws_all(self, times: int = 1):
+        """Advance the draw counters of *every* node (all nodes draw in lockstep;
+        each rank mirrors the whole network so epoch/forward-count metrics and the
+        dynamic-graph schedule need no communication)."""
+        for g in range(self.N):
+            self._count_draw(g, times)
+
+    def plan_graphs(self, oits: int, k0: int, draws_per_round: int, init_draws: int = 0, refresh: bool = True):
+        """Communication graph of every round ``0..oits-1`` (static here).  Problems
+        with a data-driven graph override this; it is what lets a dynamic topology
+        live in device tables indexed by the round counter."""
+        return [self.graph] * oits
+
     def _batch(self, g: int):
         l = self.placement.local_index(g)
         shard = self.shards.shard(l)
@@ -168,6 +181,9 @@ class ConsensusProblem:
             grads = torch.autograd.grad(loss, list(self.models[g].parameters()))
             self.arena.set_row_from_grads(l, grads)
             self.last_losses[l] = loss.detach()
+        for g in range(self.N):  # mirror the lockstep draws of nodes hosted elsewhere
+            if not self.placement.is_local(g):
+                self._count_draw(g)
         return self.last_losses
 
     # ------------------------------------------------------------------
@@ -188,7 +204,7 @@ class ConsensusProblem:
         return self.ctx.all_gather_cat(local, self.placement.counts)
 
     def all_theta(self) -> torch.Tensor:
-        return self.gather_rows(self.arena.theta)[:, : self.n]
+        return self.arena.compact(self.gather_rows(self.arena.theta))
 
     # ------------------------------------------------------------------
     # metrics

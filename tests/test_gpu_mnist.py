@@ -1,0 +1,137 @@
+"""GPU numerics: fused sm_100a kernels vs plain PyTorch fp32 references."""
+import copy
+
+import networkx as nx
+import numpy as np
+import pytest
+import torch
+
+from nn_distributed_training_b200.data.mnist import synthetic_mnist
+from nn_distributed_training_b200.data.sampler import BatchSchedule
+from nn_distributed_training_b200.models import MNISTConvNet
+from nn_distributed_training_b200.optimizers import DiNNO, DSGD, DSGT
+from nn_distributed_training_b200.problems.dist_mnist_problem import DistMNISTProblem
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+METRICS = ["forward_pass_count", "validation_loss", "consensus_error", "top1_accuracy", "current_epoch"]
+
+
+def _problem(N, B, backend, opt_conf, M=300, float_inputs=False, seed=0, graph=None, eval_every=1000):
+    torch.manual_seed(seed)
+    data = synthetic_mnist(M * N, seed=3)
+    val = synthetic_mnist(200, seed=4)
+    shards = [data.select(torch.arange(i * M, (i + 1) * M)) for i in range(N)]
+    if float_inputs:
+        from nn_distributed_training_b200.data.shards import Shard
+        shards = [Shard(s.inputs(torch.arange(len(s)), torch.float32), s.y) for s in shards]
+        val = Shard(val.inputs(torch.arange(len(val)), torch.float32), val.y)
+    conf = {"problem_name": "t", "train_batch_size": B, "val_batch_size": 64, "metrics": METRICS,
+            "metrics_config": {"evaluate_frequency": eval_every}, "optimizer_config": opt_conf}
+    return DistMNISTProblem(graph or nx.cycle_graph(N), MNISTConvNet(3, 5, 64), torch.nn.NLLLoss(),
+                            shards, val, DEV, conf, backend=backend, seed=7)
+
+
+def test_extension_loaded():
+    from nn_distributed_training_b200.ops import load_ext
+    assert load_ext(required=True) is not None
+
+
+@pytest.mark.parametrize("m,B", [(300, 64), (64, 64), (1000, 37), (5, 8)])
+def test_device_sampler_matches_python(m, B):
+    from nn_distributed_training_b200.ops import load_ext
+    ext = load_ext(required=True)
+    out = torch.zeros(B, dtype=torch.int32, device=DEV)
+    size = torch.zeros(1, dtype=torch.int32, device=DEV)
+    sched = BatchSchedule(m, B)
+    for call in [0, 1, 4, 17, 123]:
+        ext.debug_batch_indices(m, B, call, 7, 5, out.data_ptr(), size.data_ptr())
+        ref = sched.indices(call, 7, 5)
+        n = int(size.item())
+        assert n == len(ref)
+        assert out[:n].cpu().tolist() == ref.tolist()
+
+
+@pytest.mark.parametrize("B,float_inputs", [(64, False), (24, False), (64, True), (100, False)])
+def test_fwdbwd_matches_autograd(B, float_inputs):
+    conf = {"alg_name": "dsgd", "alpha0": 0.01, "mu": 0.001, "outer_iterations": 2, "profile": False}
+    fused = _problem(3, B, "fused", conf, M=150, float_inputs=float_inputs)
+    ref = _problem(3, B, "torch", conf, M=150, float_inputs=float_inputs)
+    assert fused.backend == "fused" and ref.backend == "torch"
+    ref.arena.theta.copy_(fused.arena.theta)
+    for step in range(4):  # crosses an epoch boundary (partial batch) when B does not divide 150
+        lf = fused.compute_grads().clone()
+        lr = ref.compute_grads().clone()
+        torch.testing.assert_close(lf, lr, rtol=2e-4, atol=2e-5)
+        torch.testing.assert_close(fused.arena.grad, ref.arena.grad, rtol=2e-3, atol=2e-5)
+    assert fused.forward_cnt == ref.forward_cnt
+    assert (fused.calls == ref.calls).all()
+
+
+def test_eval_matches_torch():
+    conf = {"alg_name": "dsgd", "alpha0": 0.01, "mu": 0.001, "outer_iterations": 2, "profile": False}
+    fused = _problem(3, 64, "fused", conf)
+    ref = _problem(3, 64, "torch", conf)
+    ref.arena.theta.copy_(fused.arena.theta)
+    pf, of = fused._validate_local()
+    prf, orf = ref._validate_local()
+    torch.testing.assert_close(pf, prf, rtol=2e-4, atol=2e-5)
+    assert (of != orf).float().mean().item() < 0.01
+    fused.evaluate_metrics()
+    ref.evaluate_metrics()
+    torch.testing.assert_close(fused.metrics["validation_loss"][0], ref.metrics["validation_loss"][0],
+                               rtol=1e-4, atol=1e-6)
+
+
+DINNO = {"alg_name": "dinno", "rho_init": 0.5, "rho_scaling": 1.01, "outer_iterations": 7,
+         "primal_iterations": 2, "primal_optimizer": "adam", "persistant_primal_opt": False,
+         "primal_lr_start": 0.005, "primal_lr_finish": 0.0005, "lr_decay_type": "log", "profile": False}
+DSGD_C = {"alg_name": "dsgd", "alpha0": 0.05, "mu": 0.01, "outer_iterations": 7, "profile": False}
+DSGT_C = {"alg_name": "dsgt", "alpha": 0.02, "init_grads": True, "outer_iterations": 7, "profile": False}
+
+
+@pytest.mark.parametrize("cls,conf", [(DiNNO, DINNO), (DiNNO, dict(DINNO, primal_optimizer="sgd")),
+                                      (DiNNO, dict(DINNO, primal_optimizer="adamw", persistant_primal_opt=True)),
+                                      (DSGD, DSGD_C), (DSGT, DSGT_C), (DSGT, dict(DSGT_C, init_grads=False))])
+@pytest.mark.parametrize("graph", ["cycle", "wheel"])
+def test_fused_training_matches_torch_ops(cls, conf, graph):
+    """Whole fused round programs (CUDA graph replay) vs the PyTorch consensus ops driving
+    the same fused forward/backward, 7 rounds, fp32."""
+    N = 5
+    G = nx.cycle_graph(N) if graph == "cycle" else nx.wheel_graph(N)
+    a = _problem(N, 32, "fused", conf, graph=G, eval_every=3)
+    b = _problem(N, 32, "fused", conf, graph=G, eval_every=3)
+    b.arena.theta.copy_(a.arena.theta)
+    oa = cls(a, DEV, copy.deepcopy(conf))
+    ob = cls(b, DEV, dict(copy.deepcopy(conf), consensus_backend="torch"))
+    oa.train()
+    ob.train()
+    torch.testing.assert_close(a.arena.theta, b.arena.theta, rtol=2e-3, atol=2e-5)
+    assert a.forward_cnt == b.forward_cnt
+    assert len(a.metrics["validation_loss"]) == len(b.metrics["validation_loss"]) == 4
+    if cls is DSGT:
+        torch.testing.assert_close(oa.y, ob.y, rtol=2e-3, atol=2e-5)
+
+
+def test_consensus_kernels_fp64_with_autograd_model():
+    """fp64 arena on the GPU: autograd forward/backward + fused fp64 consensus kernels (eager)."""
+    torch.manual_seed(0)
+    N, B = 4, 16
+    g = torch.Generator().manual_seed(0)
+    train = [torch.utils.data.TensorDataset(torch.randn(B, 1, 28, 28, generator=g, dtype=torch.float64),
+                                            torch.randint(0, 10, (B,), generator=g)) for _ in range(N)]
+    val = torch.utils.data.TensorDataset(torch.randn(32, 1, 28, 28, generator=g, dtype=torch.float64),
+                                         torch.randint(0, 10, (32,), generator=g))
+    outs = []
+    for backend in ("auto", "torch"):
+        conf = dict(DINNO, consensus_backend=backend)
+        pconf = {"problem_name": "t", "train_batch_size": B, "val_batch_size": 16, "metrics": METRICS,
+                 "metrics_config": {"evaluate_frequency": 100}, "optimizer_config": conf}
+        torch.manual_seed(1)
+        pr = DistMNISTProblem(nx.wheel_graph(N), MNISTConvNet(3, 5, 64, dtype=torch.float64), torch.nn.NLLLoss(),
+                              train, val, DEV, pconf)
+        assert pr.backend == "torch"
+        DiNNO(pr, DEV, conf).train()
+        outs.append(pr.arena.theta.clone())
+    bad = (outs[0] - outs[1]).abs() > 1e-8 + 1e-6 * outs[1].abs()
+    assert bad.double().mean().item() < 1e-3
