@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""Headline benchmark: consensus rounds/sec of DiNNO on the dist_mnist_PAPER config.
+
+    python bench.py --gpus N --steps K --warmup W [--impl ours|reference]
+    (N > 1: launched by the driver through torch.distributed.run, one rank per GPU)
+
+Config (reference: experiments/dist_mnist_PAPER.yaml problem1): MNISTConvNet(3,5,64),
+DiNNO rho0=0.5 x1.0003/round, 2 primal Adam steps/round (lr log 5e-3 -> 5e-4, moments reset
+every round), batch 64, cycle graph, one class per node (hetero split).  Weak scaling: every
+GPU hosts 10 graph nodes, so N GPUs train a 10*N-node cycle (the node range of the
+reference's own scaling experiment, experiments/dist_mnist_scaling.yaml: 10..100 nodes).
+A *step* is one communication round of the whole network.  ``value`` is node-rounds/sec =
+rounds/sec x number of graph nodes (whole job).  Synthetic MNIST-shaped uint8 data and
+random-init weights (no dataset can be downloaded); evaluation is excluded from the timed
+region in both arms.
+
+* ``value``  — device-timed (CUDA events on the launching stream, max over ranks), shards
+  resident in HBM (the framework's native pipeline); each GPU's shard set is sized > L2 and
+  rows are gathered at random, so inputs are not L2-resident between iterations.
+* ``e2e``    — same metric through the public API ``DiNNO(problem, device, conf).train()``
+  with the host-fed input pipeline: every round copies that round's minibatches from
+  pinned host memory (H2D) and reads the per-node losses back (D2H).
+* ``--impl reference`` — the unmodified reference (baseline/_ref) through its own public API
+  (DistMNISTProblem + DiNNO(...).train(profiler=hook)), stock fp64, all nodes on one device.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+NODES_PER_GPU = 10
+BATCH = 64
+PITS = 2
+SAMPLES_PER_NODE = 22000          # 10 nodes x 22000 x 784 B = 172 MB of uint8 rows per GPU (> 126 MB L2)
+REF_SAMPLES_PER_NODE = 6000       # the paper's 60000 / 10 (the reference streams from host memory anyway)
+PAPER_ROUNDS = 2000
+
+
+def opt_conf(outer_iterations: int):
+    return {"alg_name": "dinno", "rho_init": 0.5, "rho_scaling": 1.0003, "outer_iterations": outer_iterations,
+            "primal_iterations": PITS, "primal_optimizer": "adam", "persistant_primal_opt": False,
+            "primal_lr_start": 0.005, "primal_lr_finish": 0.0005, "lr_decay_type": "log", "profile": False}
+
+
+def prob_conf(oc, eval_every, extra=None):
+    c = {"problem_name": "dinno", "train_batch_size": BATCH, "val_batch_size": 128, "verbose_evals": True,
+         "metrics": ["forward_pass_count", "validation_loss", "consensus_error", "top1_accuracy", "current_epoch"],
+         "metrics_config": {"evaluate_frequency": eval_every}, "optimizer_config": oc}
+    c.update(extra or {})
+    return c
+
+
+# ------------------------------------------------------------------ clocks ----
+class ClockSampler:
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self._h = None
+        self._t = threading.Thread(target=self._loop, daemon=True)
+
+    def _once(self):
+        if self._h is None:
+            return
+        nv = self._nv
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h) if hasattr(
+                nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+                     0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+            for bit, name in names.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:  # noqa: BLE001
+            pass
+
+    def _loop(self):
+        while not self._stop.is_set():
+            self._once()
+            time.sleep(0.002)
+
+    def start(self):
+        self._once()
+        self._t.start()
+
+    def stop(self):
+        self._once()
+        self._stop.set()
+        self._t.join(timeout=1)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+class StepTimer:
+    """``profiler.step()`` hook: records a CUDA event after every round; the timed region is
+    rounds [warmup, warmup+steps)."""
+
+    def __init__(self, warmup, steps, on_start=None, on_stop=None):
+        import torch
+        self.torch = torch
+        self.warmup, self.steps = warmup, steps
+        self.count = 0
+        self.ev0 = self.ev1 = None
+        self.on_start, self.on_stop = on_start, on_stop
+        self.wall = None
+
+    def step(self):
+        torch = self.torch
+        self.count += 1
+        if self.count == self.warmup:
+            if self.on_start:
+                self.on_start()
+            torch.cuda.synchronize()
+            self._t0 = time.perf_counter()
+            self.ev0 = torch.cuda.Event(enable_timing=True)
+            self.ev0.record()
+        elif self.count == self.warmup + self.steps:
+            self.ev1 = torch.cuda.Event(enable_timing=True)
+            self.ev1.record()
+            torch.cuda.synchronize()
+            self.wall = time.perf_counter() - self._t0
+            if self.on_stop:
+                self.on_stop()
+
+    def ms(self):
+        return self.ev0.elapsed_time(self.ev1)
+
+
+# -------------------------------------------------------------------- ours ----
+def build_problem(ctx, n_nodes, oc, eval_every, extra=None, samples_per_node=SAMPLES_PER_NODE):
+    import networkx as nx
+    import torch
+    from nn_distributed_training_b200.data.mnist import synthetic_mnist
+    from nn_distributed_training_b200.data.shards import Shard
+    from nn_distributed_training_b200.models import MNISTConvNet
+    from nn_distributed_training_b200.parallel.context import Placement
+    from nn_distributed_training_b200.problems.dist_mnist_problem import DistMNISTProblem
+
+    pl = Placement(n_nodes, ctx.world_size, ctx.rank)
+    train = []
+    for g in range(n_nodes):
+        if pl.is_local(g):
+            train.append(synthetic_mnist(samples_per_node, seed=100 + g, classes=[g % 10]))
+        else:
+            train.append(_Stub(samples_per_node))
+    val = synthetic_mnist(10000, seed=1)
+    torch.manual_seed(0)
+    base = MNISTConvNet(3, 5, 64)
+    return DistMNISTProblem(nx.cycle_graph(n_nodes), base, torch.nn.NLLLoss(), train, val, ctx.device,
+                            prob_conf(oc, eval_every, extra), ctx=ctx, backend="fused")
+
+
+class _Stub:
+    def __init__(self, n):
+        self.n = n
+
+    def __len__(self):
+        return self.n
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from nn_distributed_training_b200.optimizers import DiNNO
+    from nn_distributed_training_b200.parallel.context import DistContext
+
+    ctx = DistContext.from_env(use_cuda=True)
+    assert ctx.world_size == args.gpus, f"launched with WORLD_SIZE={ctx.world_size} but --gpus {args.gpus}"
+    n_nodes = NODES_PER_GPU * args.gpus
+    W, K = args.warmup, args.steps
+    oits = max(PAPER_ROUNDS, 2 * (W + K) + 64)
+    dev = ctx.device
+
+    def maxreduce(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        return float(ctx.all_reduce_max(t).item())
+
+    # ---------------- device-timed, resident shards ----------------------------
+    pr = build_problem(ctx, n_nodes, opt_conf(oits), eval_every=10 ** 9)
+    opt = DiNNO(pr, dev, pr.conf["optimizer_config"])
+    chunk = min(K, 64)
+    rem = K % chunk
+    opt.run_rounds(max(W, 3))            # warm-up (captures the graphs used below)
+    opt.run_rounds(chunk)
+    if rem:
+        opt.run_rounds(rem)
+    sampler = ClockSampler(dev.index or 0)
+    torch.cuda.synchronize()
+    ctx.barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    opt.run_rounds(K)
+    e1.record()
+    torch.cuda.synchronize()
+    ctx.barrier()
+    clocks = sampler.stop()
+    ms = maxreduce(e0.elapsed_time(e1))
+    launches = K * 2 * PITS
+    # model quality after the rounds run so far (not timed)
+    pr.evaluate_metrics()
+    acc = float(pr.metrics["top1_accuracy"][-1].mean())
+    rounds_done = opt.k
+    opt._program.eng.check()
+    del opt, pr
+    torch.cuda.empty_cache()
+
+    # ---------------- end to end through the public API, host-fed inputs -------
+    e2e = None
+    try:
+        W2 = max(W, 6)
+        pr2 = build_problem(ctx, n_nodes, opt_conf(W2 + K + 1), eval_every=10 ** 9,
+                            extra={"input_pipeline": "host"})
+        opt2 = DiNNO(pr2, dev, pr2.conf["optimizer_config"])
+        timer = StepTimer(W2, K, on_start=ctx.barrier)
+        opt2.train(profiler=timer)
+        ctx.barrier()
+        ms2 = maxreduce(timer.ms())
+        hf = pr2.fused.host_feed
+        pr2.fused.loader.stop()
+        e2e = {"value": n_nodes * K / (ms2 / 1e3), "unit": "node-rounds/s", "ms_per_step": ms2 / K,
+               "h2d_bytes_per_step": int(hf["h2d_bytes"]), "d2h_bytes_per_step": int(hf["d2h_bytes"]),
+               "api": "DiNNO(problem, device, conf).train(profiler=hook), input_pipeline=host",
+               "wall_ms_per_step": maxreduce(timer.wall * 1e3) / K}
+        del opt2, pr2
+    except Exception as e:  # noqa: BLE001
+        e2e = {"error": repr(e)[:300]}
+
+    if ctx.is_main:
+        out = {
+            "metric": "consensus node-rounds/sec (DiNNO, dist_mnist_PAPER; rounds/sec x graph nodes)",
+            "value": n_nodes * K / (ms / 1e3), "unit": "node-rounds/s", "n_gpus": args.gpus, "steps": K,
+            "warmup": max(W, 3) + chunk + rem, "ms_per_step": ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "impl": "ours",
+            "config": {"model": "MNISTConvNet(3,5,64) 28440 params", "yaml": "dist_mnist_PAPER.yaml/problem1 (DiNNO)",
+                       "graph": f"cycle, {n_nodes} nodes ({NODES_PER_GPU} per GPU)", "global_batch": BATCH * n_nodes,
+                       "primal_iterations": PITS, "seq_len": None, "parallelism": f"consensus graph, {NODES_PER_GPU} nodes/GPU x {args.gpus} GPU",
+                       "rounds_per_sec": K / (ms / 1e3), "eval": "excluded from timed region",
+                       "l2": f"inputs {NODES_PER_GPU * SAMPLES_PER_NODE * 784 / 1e6:.0f} MB/GPU > L2, random row gather; no flush",
+                       "compute": "fp32 CUDA-core fused fwd/bwd + fused consensus kernels (reference runs fp64)"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "extra": {"top1_after_rounds": acc, "rounds_done": rounds_done},
+        }
+        print(json.dumps(out))
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------- reference ----
+def ensure_reference():
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "optimizers")):
+        subprocess.run(["bash", os.path.join(ROOT, "baseline", "install_reference.sh")],
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return ref if os.path.isdir(os.path.join(ref, "optimizers")) else None
+
+
+def run_reference(args):
+    ref = ensure_reference()
+    if ref is None:
+        print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref missing and /root/reference not mounted"}))
+        return
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world > 1:
+        # the reference has no multi-process / multi-GPU mode: rank 0 simulates every node on
+        # its GPU (the stock path), the other ranks only join the barriers.
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    if rank == 0:
+        _reference_rank0(args, ref)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _reference_rank0(args, ref):
+    import numpy as np
+    import torch
+    sys.path.insert(0, ref)
+    torch.set_default_dtype(torch.float64)   # what the stock runner does on import (experiments/dist_mnist_ex.py:19)
+    from models.mnist_conv_nn import MNISTConvNet
+    from optimizers.dinno import DiNNO
+    from problems.dist_mnist_problem import DistMNISTProblem
+    from utils import graph_generation
+    from nn_distributed_training_b200.data.mnist import synthetic_mnist, MNIST_MEAN, MNIST_STD
+
+    class U8Images(torch.utils.data.Dataset):
+        """uint8 images -> normalised default-dtype tensors per item (the job torchvision's
+        ToTensor+Normalize transform does in the stock runner)."""
+
+        def __init__(self, shard):
+            self.x, self.y = shard.x, shard.y
+
+        def __len__(self):
+            return self.x.shape[0]
+
+        def __getitem__(self, i):
+            return ((self.x[i].to(torch.get_default_dtype()) / 255.0) - MNIST_MEAN) / MNIST_STD, int(self.y[i])
+
+    n_nodes = NODES_PER_GPU * args.gpus
+    W, K = args.warmup, args.steps
+    device = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+    N, graph = graph_generation.generate_from_conf({"num_nodes": n_nodes, "type": "cycle", "p": 0.3, "gen_attempts": 100})
+    train = [U8Images(synthetic_mnist(REF_SAMPLES_PER_NODE, seed=100 + g, classes=[g % 10])) for g in range(N)]
+    val = U8Images(synthetic_mnist(10000, seed=1))
+    torch.manual_seed(0)
+    base = MNISTConvNet(3, 5, 64)
+    oc = opt_conf(W + K + 1)
+    pc = prob_conf(oc, 10 ** 9)
+    prob = DistMNISTProblem(graph, base, torch.nn.NLLLoss(), train, val, device, pc)
+    dopt = DiNNO(prob, device, oc)
+    sampler = ClockSampler(0)
+    timer = StepTimer(W, K, on_start=sampler.start)
+    dopt.train(profiler=timer)     # evaluates at k=0 (before warm-up) and at the last, untimed, round
+    clocks = sampler.stop()
+    ms = timer.ms()
+    h2d = N * PITS * BATCH * (784 * 8 + 8)
+    out = {"metric": "consensus node-rounds/sec (DiNNO, dist_mnist_PAPER; rounds/sec x graph nodes)",
+           "value": N * K / (ms / 1e3), "unit": "node-rounds/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
+           "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "fp64", "data": "synthetic", "impl": "reference",
+           "config": {"model": "MNISTConvNet(3,5,64) 28440 params", "yaml": "dist_mnist_PAPER.yaml/problem1 (DiNNO)",
+                      "graph": f"cycle, {N} nodes (all simulated on one device: the reference's only mode)",
+                      "global_batch": BATCH * N, "primal_iterations": PITS, "seq_len": None,
+                      "parallelism": "single process, single device", "rounds_per_sec": K / (ms / 1e3),
+                      "eval": "excluded from timed region", "l2": "inputs streamed from host memory every step"},
+           "clocks": clocks,
+           "e2e": {"value": N * K / (ms / 1e3), "unit": "node-rounds/s", "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": 0, "note": "stock path already feeds every batch from host memory"},
+           "gpu_launches": None}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if "--steps" not in " ".join(sys.argv):
+            args.steps = 100
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -20,8 +20,9 @@ from .shards import Shard
 MNIST_MEAN, MNIST_STD = 0.1307, 0.3081
 
 
-def synthetic_mnist(num: int, seed: int = 0, noise: float = 0.35) -> Shard:
-    """Class-conditional strokes + noise, uint8 ``[num,1,28,28]`` / int64 labels."""
+def synthetic_mnist(num: int, seed: int = 0, noise: float = 0.35, classes=None) -> Shard:
+    """Class-conditional strokes + noise, uint8 ``[num,1,28,28]`` / int64 labels.
+    ``classes`` restricts the labels (e.g. one class per node for the hetero split)."""
     g = torch.Generator().manual_seed(1234)  # prototypes are shared by train and val
     protos = torch.zeros(10, 28, 28)
     for c in range(10):
@@ -34,7 +35,7 @@ def synthetic_mnist(num: int, seed: int = 0, noise: float = 0.35) -> Shard:
                     protos[c, yi - 1: yi + 2, xi - 1: xi + 2] += 0.5
     protos.clamp_(0, 1)
     rng = np.random.default_rng(seed)
-    labels = rng.integers(0, 10, num)
+    labels = rng.integers(0, 10, num) if classes is None else np.asarray(classes)[rng.integers(0, len(classes), num)]
     combo = rng.integers(0, 25, num)  # one of 25 translations in [-2, 2]^2
     pn = protos.numpy()
     rolled = np.stack([np.roll(pn, (c // 5 - 2, c % 5 - 2), (1, 2)) for c in range(25)])  # [25,10,28,28]

@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(THREADS, 1) mnist_kernel(const Args a) {
   int shard_off = 0;
   if (TRAIN) {
     if (a.direct) {
-      bs = a.batch;
+      bs = a.direct_bs != nullptr ? (uint32_t)a.direct_bs[l] : (uint32_t)a.batch;
     } else {
       m = (uint32_t)a.shard_len[l];
       shard_off = a.shard_off[l];

@@ -18,6 +18,7 @@ struct Args {
   float mean, inv_std;
   // sampling: direct==1 -> rows [l*batch + t]; else stateless permutation of shard l
   int direct, batch, seed, node0;
+  const int* direct_bs;   // [L] valid rows per node when direct (nullptr: all `batch`)
   const int* shard_off;   // [L]
   const int* shard_len;   // [L]
   const int* calls;       // [L] draw counter per node (device, advanced by the update kernel)

@@ -51,7 +51,7 @@ class FusedMnist:
             spb=SPB, S=self.S)
         self.train_op = self.ext.MnistOp(self.base)
         self._setup_eval()
-        self._direct_op = None
+        self.host_feed = None
 
     # ---- training ---------------------------------------------------------
     def launch(self):
@@ -73,14 +73,55 @@ class FusedMnist:
         pl = self.pr.placement
         self.calls.copy_(torch.as_tensor(self.pr.calls[pl.lo: pl.lo + pl.L].astype(np.int32)))
 
-    # ---- host-fed batches (end-to-end mode) --------------------------------
-    def direct_op(self, x_stage: torch.Tensor, y_stage: torch.Tensor):
-        """Kernel op reading one staged batch per node from ``x_stage [L,B,784]`` /
-        ``y_stage [L,B]`` (filled by an H2D copy) instead of the resident shards."""
-        d = dict(self.base)
-        d.update(direct=1, x=x_stage.data_ptr(), y=y_stage.data_ptr(),
-                 x_is_u8=int(x_stage.dtype == torch.uint8))
-        return self.ext.MnistOp(d)
+    # ---- host-fed batches (end-to-end input pipeline) -----------------------
+    def enable_host_feed(self, steps_per_round: int, nslots: int = 4, threads: int = 4):
+        """Switch to the host-fed input pipeline: the dataset stays in host memory, a
+        native multi-threaded loader (csrc/runtime.cpp) assembles every round's
+        minibatches into a ring of pinned slots, and each round performs one H2D copy
+        of its inputs and one D2H read of its losses.  This is the path ``bench.py``
+        times end to end; the default pipeline keeps shards resident in HBM."""
+        pr, dev = self.pr, self.pr.device
+        P, L, B = int(steps_per_round), self.L, self.B
+        xb = 1 if self.x_is_u8 else 4
+        self.host_x = self.x.cpu().contiguous()
+        self.host_y = self.y.cpu().contiguous()
+        kw = dict(pin_memory=True)
+        self.x_pin = torch.empty(nslots, P, L, B, 784, dtype=self.x.dtype, **kw)
+        self.y_pin = torch.empty(nslots, P, L, B, dtype=torch.int64, **kw)
+        self.bs_pin = torch.empty(nslots, P, L, dtype=torch.int32, **kw)
+        self.x_stage = torch.zeros(P, L, B, 784, dtype=self.x.dtype, device=dev)
+        self.y_stage = torch.zeros(P, L, B, dtype=torch.int64, device=dev)
+        self.bs_stage = torch.zeros(P, L, dtype=torch.int32, device=dev)
+        self.loss_host = torch.zeros(L, self.S, dtype=torch.float32, **kw)
+        self.direct_ops = []
+        for p in range(P):
+            d = dict(self.base)
+            d.update(direct=1, x=self.x_stage[p].data_ptr(), y=self.y_stage[p].data_ptr(),
+                     direct_bs=self.bs_stage[p].data_ptr())
+            self.direct_ops.append(self.ext.MnistOp(d))
+        pl = pr.placement
+        calls0 = [int(c) for c in pr.calls[pl.lo: pl.lo + pl.L]]
+        self.loader = self.ext.HostBatchLoader(
+            self.host_x.data_ptr(), self.host_y.data_ptr(), 784 * xb,
+            [int(o) for o in pr.shards.offsets[:-1]], [int(m) for m in pr.shards.sizes], calls0,
+            B, P, pr.seed, pl.lo,
+            [self.x_pin[s].data_ptr() for s in range(nslots)],
+            [self.y_pin[s].data_ptr() for s in range(nslots)],
+            [self.bs_pin[s].data_ptr() for s in range(nslots)], threads)
+        self.host_feed = dict(P=P, nslots=nslots,
+                              h2d_bytes=P * L * B * (784 * xb + 8) + P * L * 4,
+                              d2h_bytes=L * self.S * 4)
+        return self.host_feed
+
+    def stage_copy(self, slot: int):
+        """Enqueue this round's H2D input copy (pinned ring slot -> device staging)."""
+        self.x_stage.copy_(self.x_pin[slot], non_blocking=True)
+        self.y_stage.copy_(self.y_pin[slot], non_blocking=True)
+        self.bs_stage.copy_(self.bs_pin[slot], non_blocking=True)
+
+    def loss_readback(self):
+        """Enqueue the D2H read of the round's per-node losses."""
+        self.loss_host.copy_(self.loss_part, non_blocking=True)
 
     # ---- validation ---------------------------------------------------------
     def _setup_eval(self):

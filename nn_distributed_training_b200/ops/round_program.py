@@ -26,15 +26,15 @@ def _round_ops(opt, eng, grads):
     alg = opt.alg_name
     if alg == "dinno":
         for p in range(opt.pits):
-            grads()
+            grads(p)
             eng.op.dinno_update(p)
     elif alg == "dsgd":
         eng.op.dsgd_mix()
-        grads()
+        grads(0)
         eng.op.dsgd_step()
     elif alg == "dsgt":
         eng.op.dsgt_mix()
-        grads()
+        grads(0)
         eng.op.dsgt_track()
     else:  # pragma: no cover
         raise NameError("Unknown distributed opt algorithm.")
@@ -58,15 +58,27 @@ class RoundProgram:
         self.graph_plan = graphs
         self.capturable = pr.fused is not None
         self._graphs: Dict[int, torch.cuda.CUDAGraph] = {}
+        self.host_mode = False
         if self.capturable:
             pr.fused.sync_calls_from_host()
+            if pr.conf.get("input_pipeline", "resident") == "host":
+                if init_draws:
+                    raise NotImplementedError("host-fed pipeline with DSGT init_grads")
+                pr.fused.enable_host_feed(self.dpr, nslots=int(pr.conf.get("host_slots", 4)),
+                                          threads=int(pr.conf.get("host_threads", 4)))
+                self.host_mode = True
+                self._slot_graphs: Dict[int, torch.cuda.CUDAGraph] = {}
+                self._slot_events = {}
+                self._inflight = []
 
-    def grads(self):
+    def grads(self, p: int = 0):
         pr = self.pr
-        if pr.fused is not None:
-            pr.fused.launch()
-        else:
+        if pr.fused is None:
             pr.compute_grads()
+        elif self.host_mode:
+            pr.fused.direct_ops[p].train()
+        else:
+            pr.fused.launch()
 
     def _count(self, rounds: int):
         """Host mirror of the device-side draw counters."""
@@ -79,8 +91,34 @@ class RoundProgram:
         if self.pr.fused is not None:
             self.pr.count_draws_all(1)
 
+    def _run_host_fed(self, rounds: int):
+        """One graph replay per round: H2D copy of the round's inputs from the pinned
+        ring slot, the round's kernels, D2H read of the losses."""
+        fz = self.pr.fused
+        for _ in range(rounds):
+            while len(self._inflight) >= fz.host_feed["nslots"] - 1:
+                s_old, ev = self._inflight.pop(0)
+                ev.synchronize()          # its H2D copy is done: the loader may refill the slot
+                fz.loader.release(s_old)
+            slot = fz.loader.acquire()
+            g = self._slot_graphs.get(slot)
+            if g is None:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    fz.stage_copy(slot)
+                    _round_ops(self.opt, self.eng, self.grads)
+                    fz.loss_readback()
+                self._slot_graphs[slot] = g
+            g.replay()
+            ev = torch.cuda.Event()
+            ev.record()
+            self._inflight.append((slot, ev))
+            self._count(1)
+
     def run(self, rounds: int):
         """Execute ``rounds`` consecutive rounds starting at the device round counter."""
+        if self.host_mode:
+            return self._run_host_fed(rounds)
         left = rounds
         while left > 0:
             r = min(left, MAX_ROUNDS_PER_GRAPH)
@@ -114,8 +152,9 @@ class RoundProgram:
 
 def run_fused_training(opt, profiler=None):
     pr = opt.pr
-    prog = RoundProgram(opt)
-    opt._program = prog
+    prog = getattr(opt, "_program", None)
+    if prog is None:
+        prog = opt._program = RoundProgram(opt)
     if opt.alg_name == "dsgt" and opt.init_grads and not opt._initialised:
         prog.dsgt_init()
     if opt.alg_name == "dsgt":

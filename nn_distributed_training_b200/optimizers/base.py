@@ -135,6 +135,29 @@ class ConsensusOptimizer:
     def _before_training(self):
         pass
 
+    def run_rounds(self, n: int):
+        """Advance ``n`` communication rounds with no evaluation in between (the
+        stepping API used by benchmarks and custom training loops)."""
+        n = min(int(n), self.oits - self.k)
+        if n <= 0:
+            return
+        if self._use_engine():
+            from ..ops.round_program import RoundProgram
+            prog = getattr(self, "_program", None)
+            if prog is None:
+                prog = self._program = RoundProgram(self)
+                if self.alg_name == "dsgt":
+                    if self.init_grads and not self._initialised:
+                        prog.dsgt_init()
+                    self._initialised = True
+            prog.run(n)
+            self.k += n
+        else:
+            self._before_training()
+            for _ in range(n):
+                self._round(self.k)
+                self.k += 1
+
     def _use_engine(self) -> bool:
         """Fused sm_100a consensus kernels: any arena problem on a CUDA device with the
         synchronous (Jacobi) update order; the PyTorch ops remain for CPU/gloo, for
