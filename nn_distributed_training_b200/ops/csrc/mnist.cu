@@ -28,17 +28,24 @@ constexpr int FC1_IN = 432, HID = 64, NCLS = 10;
 constexpr int W1_STRIDE = 436;          // padded fc1 row stride in smem (floats)
 constexpr int XROW = 22;                // padded row stride of the even/odd column planes
 constexpr int XPLANE = HW * XROW;       // 616 floats per plane
-constexpr int THREADS = 256;
-constexpr int KSLICES = 4, K4_PER_SLICE = FC1_IN / 4 / KSLICES;  // 27 float4 per k-slice
+constexpr int CGROUP = 256;             // threads cooperating on one conv channel in the backward
 
-template <int SPB>
+// NT threads per CTA: 64 hidden units x (NT/64) k-slices must tile the 108 float4 of an fc1 row.
+template <int NT> struct Geo {
+  static constexpr int KSLICES = NT / 64;
+  static constexpr int K4S = (FC1_IN / 4) / KSLICES;
+  static_assert((FC1_IN / 4) % KSLICES == 0, "NT/64 must divide 108");
+  static_assert(NT >= 3 * CGROUP && NT >= FC1_IN, "need >= 768 threads");
+};
+
+template <int SPB, int NT>
 struct Smem {
-  float w1[HID * W1_STRIDE];
+  float w1[HID * W1_STRIDE];            // fc1 weights; later scratch for dW1 transposition / conv-grad reduce
   float xe[SPB * XPLANE];
   float xo[SPB * XPLANE];
   float a1[SPB * FC1_IN];
   float da1[SPB * FC1_IN];
-  float hpart[KSLICES * SPB * HID];
+  float hpart[Geo<NT>::KSLICES * SPB * HID];
   float h[SPB * HID];
   float dh[SPB * HID];
   float dhT[HID * SPB];
@@ -55,41 +62,59 @@ struct Smem {
   unsigned char arg[SPB * FC1_IN];
 };
 
-template <int SPB>
-__device__ __forceinline__ void load_images(Smem<SPB>& sm, const Args& a, int tid) {
-  // 196 groups of 4 pixels per sample; columns 4q..4q+3 of one row never straddle rows (28 % 4 == 0)
-  for (int o = tid; o < SPB * 196; o += THREADS) {
-    const int s = o / 196, q = o - s * 196;
-    const int row = (4 * q) / HW, col = (4 * q) - row * HW;
-    float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
-    if (sm.valid[s] != 0.f) {
-      const size_t base = (size_t)sm.sidx[s] * 784 + 4 * q;
-      if (a.x_is_u8) {
-        const uchar4 p = *reinterpret_cast<const uchar4*>(reinterpret_cast<const unsigned char*>(a.x) + base);
-        v0 = (p.x * (1.f / 255.f) - a.mean) * a.inv_std;
-        v1 = (p.y * (1.f / 255.f) - a.mean) * a.inv_std;
-        v2 = (p.z * (1.f / 255.f) - a.mean) * a.inv_std;
-        v3 = (p.w * (1.f / 255.f) - a.mean) * a.inv_std;
-      } else {
-        const float4 p = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.x) + base);
-        v0 = p.x; v1 = p.y; v2 = p.z; v3 = p.w;
+template <int SPB, int NT>
+__device__ __forceinline__ void load_images(Smem<SPB, NT>& sm, const Args& a, int tid) {
+  // 196 groups of 4 pixels per sample; issue every global load of this thread before the
+  // first conversion so the latencies overlap
+  constexpr int PER = (SPB * 196 + NT - 1) / NT;
+  uint32_t raw_u8[PER];
+  float4 raw_f[PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int o = tid + i * NT;
+    raw_u8[i] = 0; raw_f[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (o < SPB * 196) {
+      const int s = o / 196, q = o - s * 196;
+      if (sm.valid[s] != 0.f) {
+        const size_t base = (size_t)sm.sidx[s] * 784 + 4 * q;
+        if (a.x_is_u8) raw_u8[i] = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const unsigned char*>(a.x) + base);
+        else raw_f[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.x) + base);
       }
     }
-    float* e = sm.xe + s * XPLANE + row * XROW + (col >> 1);
-    float* d = sm.xo + s * XPLANE + row * XROW + (col >> 1);
-    e[0] = v0; d[0] = v1; e[1] = v2; d[1] = v3;
+  }
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int o = tid + i * NT;
+    if (o < SPB * 196) {
+      const int s = o / 196, q = o - s * 196;
+      const int row = (4 * q) / HW, col = (4 * q) - row * HW;
+      float v0, v1, v2, v3;
+      if (a.x_is_u8) {
+        const bool ok = sm.valid[s] != 0.f;
+        const uint32_t p = raw_u8[i];
+        v0 = ok ? ((p & 0xff) * (1.f / 255.f) - a.mean) * a.inv_std : 0.f;
+        v1 = ok ? (((p >> 8) & 0xff) * (1.f / 255.f) - a.mean) * a.inv_std : 0.f;
+        v2 = ok ? (((p >> 16) & 0xff) * (1.f / 255.f) - a.mean) * a.inv_std : 0.f;
+        v3 = ok ? ((p >> 24) * (1.f / 255.f) - a.mean) * a.inv_std : 0.f;
+      } else {
+        v0 = raw_f[i].x; v1 = raw_f[i].y; v2 = raw_f[i].z; v3 = raw_f[i].w;
+      }
+      float* e = sm.xe + s * XPLANE + row * XROW + (col >> 1);
+      float* d = sm.xo + s * XPLANE + row * XROW + (col >> 1);
+      e[0] = v0; d[0] = v1; e[1] = v2; d[1] = v3;
+    }
   }
 }
 
 // pixel (r, c) of sample s
-template <int SPB>
-__device__ __forceinline__ float px(const Smem<SPB>& sm, int s, int r, int c) {
+template <int SPB, int NT>
+__device__ __forceinline__ float px(const Smem<SPB, NT>& sm, int s, int r, int c) {
   return ((c & 1) ? sm.xo : sm.xe)[s * XPLANE + r * XROW + (c >> 1)];
 }
 
-template <int SPB>
-__device__ __forceinline__ void conv_relu_pool(Smem<SPB>& sm, int tid) {
-  for (int it = tid; it < SPB * NPOOL; it += THREADS) {
+template <int SPB, int NT>
+__device__ __forceinline__ void conv_relu_pool(Smem<SPB, NT>& sm, int tid) {
+  for (int it = tid; it < SPB * NPOOL; it += NT) {
     const int s = it / NPOOL, p = it - s * NPOOL;
     const int py = p / PHW, pxx = p - py * PHW;
     float patch[6][6];
@@ -129,16 +154,17 @@ __device__ __forceinline__ void conv_relu_pool(Smem<SPB>& sm, int tid) {
   }
 }
 
-template <int SPB>
-__device__ __forceinline__ void fc1_forward(Smem<SPB>& sm, int tid) {
+template <int SPB, int NT>
+__device__ __forceinline__ void fc1_forward(Smem<SPB, NT>& sm, int tid) {
+  constexpr int K4S = Geo<NT>::K4S;
   const int j = tid & 63, ks = tid >> 6;
   float acc[SPB];
 #pragma unroll
   for (int s = 0; s < SPB; ++s) acc[s] = 0.f;
-  const float4* wrow = reinterpret_cast<const float4*>(sm.w1 + j * W1_STRIDE) + ks * K4_PER_SLICE;
-  const float4* arow = reinterpret_cast<const float4*>(sm.a1) + ks * K4_PER_SLICE;
+  const float4* wrow = reinterpret_cast<const float4*>(sm.w1 + j * W1_STRIDE) + ks * K4S;
+  const float4* arow = reinterpret_cast<const float4*>(sm.a1) + ks * K4S;
 #pragma unroll 3
-  for (int i = 0; i < K4_PER_SLICE; ++i) {
+  for (int i = 0; i < K4S; ++i) {
     const float4 w = wrow[i];
 #pragma unroll
     for (int s = 0; s < SPB; ++s) {
@@ -150,10 +176,11 @@ __device__ __forceinline__ void fc1_forward(Smem<SPB>& sm, int tid) {
   for (int s = 0; s < SPB; ++s) sm.hpart[(ks * SPB + s) * HID + j] = acc[s];
 }
 
-template <int SPB, bool TRAIN>
-__global__ void __launch_bounds__(THREADS, 1) mnist_kernel(const Args a) {
+template <int SPB, int NT, bool TRAIN>
+__global__ void __launch_bounds__(NT, 1) mnist_kernel(const Args a) {
+  constexpr int KSLICES = Geo<NT>::KSLICES, K4S = Geo<NT>::K4S;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem<SPB>& sm = *reinterpret_cast<Smem<SPB>*>(smem_raw);
+  Smem<SPB, NT>& sm = *reinterpret_cast<Smem<SPB, NT>*>(smem_raw);
   const int tid = threadIdx.x;
   const int l = blockIdx.y;
   const float* th = a.theta + (size_t)l * a.n_pad;
@@ -161,7 +188,7 @@ __global__ void __launch_bounds__(THREADS, 1) mnist_kernel(const Args a) {
   // ---- stage fc1 weights (async) and the small tensors ----------------------------------
   {
     const float* w1g = th + a.off_w1;
-    for (int o = tid; o < HID * (FC1_IN / 4); o += THREADS) {
+    for (int o = tid; o < HID * (FC1_IN / 4); o += NT) {
       const int j = o / (FC1_IN / 4), k4 = o - j * (FC1_IN / 4);
       cp_async16(sm.w1 + j * W1_STRIDE + 4 * k4, w1g + j * FC1_IN + 4 * k4);
     }
@@ -170,7 +197,7 @@ __global__ void __launch_bounds__(THREADS, 1) mnist_kernel(const Args a) {
     if (tid < 3) sm.wc[75 + tid] = th[a.off_bc + tid];
     if (tid < HID) sm.b1[tid] = th[a.off_b1 + tid];
     if (tid < NCLS) sm.b2[tid] = th[a.off_b2 + tid];
-    for (int o = tid; o < NCLS * HID; o += THREADS) sm.w2[o] = th[a.off_w2 + o];
+    for (int o = tid; o < NCLS * HID; o += NT) sm.w2[o] = th[a.off_w2 + o];
   }
 
   // ---- batch geometry ---------------------------------------------------------------------
@@ -209,16 +236,16 @@ __global__ void __launch_bounds__(THREADS, 1) mnist_kernel(const Args a) {
       sm.label[tid] = ok != 0.f ? (int)a.y[idx] : 0;
     }
     __syncthreads();
-    load_images<SPB>(sm, a, tid);
+    load_images<SPB, NT>(sm, a, tid);
     __syncthreads();
-    conv_relu_pool<SPB>(sm, tid);
+    conv_relu_pool<SPB, NT>(sm, tid);
     cp_async_wait<0>();
     __syncthreads();
 
     // ---- fc1 -------------------------------------------------------------------------------
-    fc1_forward<SPB>(sm, tid);
+    fc1_forward<SPB, NT>(sm, tid);
     __syncthreads();
-    for (int o = tid; o < SPB * HID; o += THREADS) {
+    for (int o = tid; o < SPB * HID; o += NT) {
       const int s = o >> 6, j = o & 63;
       float v = sm.b1[j];
 #pragma unroll
@@ -271,7 +298,7 @@ __global__ void __launch_bounds__(THREADS, 1) mnist_kernel(const Args a) {
       a.loss_part[l * gridDim.x + blockIdx.x] = tot * inv_bs;
     }
     // ---- fc2 grads, dh ----------------------------------------------------------------------
-    for (int o = tid; o < NCLS * HID; o += THREADS) {
+    for (int o = tid; o < NCLS * HID; o += NT) {
       const int c = o >> 6, j = o & 63;
       float v = 0.f;
 #pragma unroll
@@ -284,7 +311,7 @@ __global__ void __launch_bounds__(THREADS, 1) mnist_kernel(const Args a) {
       for (int s = 0; s < SPB; ++s) v += sm.dz[s * 16 + tid];
       gp[a.off_b2 + tid] = v;
     }
-    for (int o = tid; o < SPB * HID; o += THREADS) {
+    for (int o = tid; o < SPB * HID; o += NT) {
       const int s = o >> 6, j = o & 63;
       float v = 0.f;
 #pragma unroll
@@ -300,104 +327,126 @@ __global__ void __launch_bounds__(THREADS, 1) mnist_kernel(const Args a) {
       for (int s = 0; s < SPB; ++s) v += sm.dh[s * HID + tid];
       gp[a.off_b1 + tid] = v;
     }
-    // ---- da1 = dh . W1 (masked by ReLU) ------------------------------------------------------
-    if (tid < FC1_IN / 2) {
-      float acc0[SPB], acc1[SPB];
+    // ---- da1 = dh . W1 (masked by ReLU): one fc1 input k per thread ---------------------------
+    if (tid < FC1_IN) {
+      float acc[SPB];
 #pragma unroll
-      for (int s = 0; s < SPB; ++s) { acc0[s] = 0.f; acc1[s] = 0.f; }
+      for (int s = 0; s < SPB; ++s) acc[s] = 0.f;
 #pragma unroll 4
       for (int j = 0; j < HID; ++j) {
-        const float2 w = *reinterpret_cast<const float2*>(sm.w1 + j * W1_STRIDE + 2 * tid);
+        const float w = sm.w1[j * W1_STRIDE + tid];
 #pragma unroll
-        for (int s = 0; s < SPB; ++s) {
-          const float d = sm.dhT[j * SPB + s];
-          acc0[s] = fmaf(d, w.x, acc0[s]);
-          acc1[s] = fmaf(d, w.y, acc1[s]);
-        }
+        for (int s = 0; s < SPB; ++s) acc[s] = fmaf(sm.dhT[j * SPB + s], w, acc[s]);
       }
 #pragma unroll
       for (int s = 0; s < SPB; ++s) {
-        const int k = s * FC1_IN + 2 * tid;
-        sm.da1[k] = sm.a1[k] > 0.f ? acc0[s] : 0.f;
-        sm.da1[k + 1] = sm.a1[k + 1] > 0.f ? acc1[s] : 0.f;
+        const int k = s * FC1_IN + tid;
+        sm.da1[k] = sm.a1[k] > 0.f ? acc[s] : 0.f;
       }
     }
-    // ---- dW1[j][k] = sum_s dh[s][j] a1[s][k]  (register tile of 108 per thread) ---------------
+    // ---- dW1[j][k] = sum_s dh[s][j] a1[s][k]: register tile per (j, k-slice) -------------------
+    float4 dw[K4S];
     {
       const int j = tid & 63, ks = tid >> 6;
-      float4 acc[K4_PER_SLICE];
 #pragma unroll
-      for (int i = 0; i < K4_PER_SLICE; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4* arow = reinterpret_cast<const float4*>(sm.a1) + ks * K4_PER_SLICE;
+      for (int i = 0; i < K4S; ++i) dw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4* arow = reinterpret_cast<const float4*>(sm.a1) + ks * K4S;
 #pragma unroll
       for (int s = 0; s < SPB; ++s) {
         const float d = sm.dh[s * HID + j];
 #pragma unroll
-        for (int i = 0; i < K4_PER_SLICE; ++i) {
+        for (int i = 0; i < K4S; ++i) {
           const float4 x = arow[s * (FC1_IN / 4) + i];
-          acc[i].x = fmaf(d, x.x, acc[i].x);
-          acc[i].y = fmaf(d, x.y, acc[i].y);
-          acc[i].z = fmaf(d, x.z, acc[i].z);
-          acc[i].w = fmaf(d, x.w, acc[i].w);
+          dw[i].x = fmaf(d, x.x, dw[i].x);
+          dw[i].y = fmaf(d, x.y, dw[i].y);
+          dw[i].z = fmaf(d, x.z, dw[i].z);
+          dw[i].w = fmaf(d, x.w, dw[i].w);
         }
       }
-      float4* out = reinterpret_cast<float4*>(gp + a.off_w1 + j * FC1_IN) + ks * K4_PER_SLICE;
+    }
+    __syncthreads();   // every read of the staged W1 is done: its smem becomes scratch
+    {
+      // transpose through smem so the global stores are fully coalesced
+      const int j = tid & 63, ks = tid >> 6;
+      float4* srow = reinterpret_cast<float4*>(sm.w1 + j * W1_STRIDE) + ks * K4S;
 #pragma unroll
-      for (int i = 0; i < K4_PER_SLICE; ++i) out[i] = acc[i];
+      for (int i = 0; i < K4S; ++i) srow[i] = dw[i];
     }
     __syncthreads();
+    {
+      float4* out = reinterpret_cast<float4*>(gp + a.off_w1);
+      for (int o = tid; o < HID * (FC1_IN / 4); o += NT) {
+        const int j = o / (FC1_IN / 4), k4 = o - j * (FC1_IN / 4);
+        out[o] = *reinterpret_cast<const float4*>(sm.w1 + j * W1_STRIDE + 4 * k4);
+      }
+    }
     // ---- conv grads: each pooled cell routes da1 to its argmax conv position ------------------
-    if (tid < 80) sm.red[tid] = 0.f;
-    __syncthreads();
-    for (int c = 0; c < F; ++c) {
-      float acc[26];
+    // 3 groups of 256 threads, one per channel; partial sums are transposed through smem
+    // (scratch = the dead W1 region) and reduced by warps — no 26x5 shuffle trees.
+    float cacc[26];
 #pragma unroll
-      for (int i = 0; i < 26; ++i) acc[i] = 0.f;
-      for (int it = tid; it < SPB * NPOOL; it += THREADS) {
+    for (int i = 0; i < 26; ++i) cacc[i] = 0.f;
+    const int cg = tid / CGROUP, ct = tid - cg * CGROUP;
+    if (cg < F) {
+      for (int it = ct; it < SPB * NPOOL; it += CGROUP) {
         const int s = it / NPOOL, p = it - s * NPOOL;
-        const float g = sm.da1[s * FC1_IN + c * NPOOL + p];
+        const float g = sm.da1[s * FC1_IN + cg * NPOOL + p];
         if (g != 0.f) {
-          const int ai = sm.arg[s * FC1_IN + c * NPOOL + p];
+          const int ai = sm.arg[s * FC1_IN + cg * NPOOL + p];
           const int py = p / PHW, pxx = p - py * PHW;
           const int r0 = 2 * py + (ai >> 1), c0 = 2 * pxx + (ai & 1);
 #pragma unroll
           for (int ky = 0; ky < KS; ++ky)
 #pragma unroll
             for (int kx = 0; kx < KS; ++kx)
-              acc[ky * 5 + kx] = fmaf(g, px<SPB>(sm, s, r0 + ky, c0 + kx), acc[ky * 5 + kx]);
-          acc[25] += g;
+              cacc[ky * 5 + kx] = fmaf(g, px<SPB, NT>(sm, s, r0 + ky, c0 + kx), cacc[ky * 5 + kx]);
+          cacc[25] += g;
         }
       }
+    }
+    __syncthreads();   // dW1 copy-out finished reading the scratch
+    float* scratch = sm.w1;   // [78][CGROUP]
+    if (cg < F) {
 #pragma unroll
-      for (int i = 0; i < 26; ++i) {
-        const float v = warp_sum(acc[i]);
-        if ((tid & 31) == 0) atomicAdd(&sm.red[i < 25 ? c * 25 + i : 75 + c], v);
-      }
+      for (int i = 0; i < 26; ++i) scratch[(cg * 26 + i) * CGROUP + ct] = cacc[i];
     }
     __syncthreads();
-    if (tid < 75) gp[a.off_wc + tid] = sm.red[tid];
-    if (tid < 3) gp[a.off_bc + tid] = sm.red[75 + tid];
+    {
+      const int warp = tid >> 5, lane = tid & 31;
+      for (int o = warp; o < 78; o += NT / 32) {
+        float v = 0.f;
+#pragma unroll
+        for (int q = 0; q < CGROUP / 32; ++q) v += scratch[o * CGROUP + lane + 32 * q];
+        v = warp_sum(v);
+        if (lane == 0) {
+          const int c = o / 26, i = o - c * 26;
+          gp[(i < 25) ? a.off_wc + c * 25 + i : a.off_bc + c] = v;
+        }
+      }
+    }
   }
 }
+
+constexpr int kNT = 768;
 
 template <int SPB, bool TRAIN>
 static cudaError_t prepare_once() {
   // opt in to >48 KB dynamic shared memory once per process (not a stream op: legal under capture)
-  static cudaError_t st = cudaFuncSetAttribute(mnist_kernel<SPB, TRAIN>,
+  static cudaError_t st = cudaFuncSetAttribute(mnist_kernel<SPB, kNT, TRAIN>,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)sizeof(Smem<SPB>));
+                                               (int)sizeof(Smem<SPB, kNT>));
   return st;
 }
 
 template <int SPB>
 static cudaError_t launch_t(const Args& a, int S, bool train, int eval_ctas, cudaStream_t st) {
-  const size_t smem = sizeof(Smem<SPB>);
+  const size_t smem = sizeof(Smem<SPB, kNT>);
   cudaError_t e = train ? prepare_once<SPB, true>() : prepare_once<SPB, false>();
   if (e != cudaSuccess) return e;
   if (train) {
-    mnist_kernel<SPB, true><<<dim3(S, a.L), THREADS, smem, st>>>(a);
+    mnist_kernel<SPB, kNT, true><<<dim3(S, a.L), kNT, smem, st>>>(a);
   } else {
-    mnist_kernel<SPB, false><<<dim3(eval_ctas, a.L), THREADS, smem, st>>>(a);
+    mnist_kernel<SPB, kNT, false><<<dim3(eval_ctas, a.L), kNT, smem, st>>>(a);
   }
   return cudaGetLastError();
 }
@@ -417,7 +466,6 @@ cudaError_t launch_batch_indices(int m, int B, int call, int seed, int node, int
 
 cudaError_t launch_train(const Args& a, int spb, int S, cudaStream_t st) {
   if (spb == 8) return launch_t<8>(a, S, true, 0, st);
-  if (spb == 4) return launch_t<4>(a, S, true, 0, st);
   return cudaErrorInvalidValue;
 }
 

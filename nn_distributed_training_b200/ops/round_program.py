@@ -13,6 +13,7 @@ eagerly around an autograd step.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict
 
 import torch
@@ -56,10 +57,10 @@ class RoundProgram:
                                 refresh=getattr(opt, "refresh_graph", True))
         self.eng = ConsensusEngine(opt, graphs)
         self.graph_plan = graphs
-        self.capturable = pr.fused is not None
+        self.capturable = pr.fused is not None and os.environ.get("NNDT_NO_GRAPH", "0") != "1"
         self._graphs: Dict[int, torch.cuda.CUDAGraph] = {}
         self.host_mode = False
-        if self.capturable:
+        if pr.fused is not None:
             pr.fused.sync_calls_from_host()
             if pr.conf.get("input_pipeline", "resident") == "host":
                 if init_draws:
