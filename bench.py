@@ -222,6 +222,7 @@ def run_ours(args):
     acc = float(pr.metrics["top1_accuracy"][-1].mean())
     rounds_done = opt.k
     opt._program.eng.check()
+    symm_how = opt._program.eng.pub_buf.how
     del opt, pr
     torch.cuda.empty_cache()
 
@@ -258,7 +259,8 @@ def run_ours(args):
                        "primal_iterations": PITS, "seq_len": None, "parallelism": f"consensus graph, {NODES_PER_GPU} nodes/GPU x {args.gpus} GPU",
                        "rounds_per_sec": K / (ms / 1e3), "eval": "excluded from timed region",
                        "l2": f"inputs {NODES_PER_GPU * SAMPLES_PER_NODE * 784 / 1e6:.0f} MB/GPU > L2, random row gather; no flush",
-                       "compute": "fp32 CUDA-core fused fwd/bwd + fused consensus kernels (reference runs fp64)"},
+                       "compute": "fp32 CUDA-core fused fwd/bwd + fused consensus kernels (reference runs fp64)",
+                       "exchange": f"in-kernel P2P pulls of neighbor rows ({symm_how} peer mapping); no NCCL on the hot path"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "extra": {"top1_after_rounds": acc, "rounds_done": rounds_done},
         }

@@ -1,0 +1,83 @@
+"""Multi-process worker (launched by torch.distributed.run from test_distributed.py).
+
+Every rank hosts N/world graph nodes; after a few rounds the gathered parameters must match
+a single-process run of the same problem (rank 0 recomputes it locally)."""
+import argparse
+import copy
+import os
+import sys
+
+import networkx as nx
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from nn_distributed_training_b200.data.mnist import synthetic_mnist  # noqa: E402
+from nn_distributed_training_b200.models import MNISTConvNet  # noqa: E402
+from nn_distributed_training_b200.optimizers import build_optimizer  # noqa: E402
+from nn_distributed_training_b200.parallel.context import DistContext  # noqa: E402
+from nn_distributed_training_b200.problems.dist_mnist_problem import DistMNISTProblem  # noqa: E402
+
+CONFS = {
+    "dinno": {"alg_name": "dinno", "rho_init": 0.5, "rho_scaling": 1.01, "outer_iterations": 6,
+              "primal_iterations": 2, "primal_optimizer": "adam", "persistant_primal_opt": False,
+              "primal_lr_start": 0.005, "primal_lr_finish": 0.0005, "lr_decay_type": "log", "profile": False},
+    "dsgd": {"alg_name": "dsgd", "alpha0": 0.05, "mu": 0.01, "outer_iterations": 6, "profile": False},
+    "dsgt": {"alg_name": "dsgt", "alpha": 0.02, "init_grads": True, "outer_iterations": 6, "profile": False},
+}
+METRICS = ["forward_pass_count", "validation_loss", "consensus_error", "top1_accuracy", "current_epoch"]
+
+
+def build(ctx, N, graph, conf, backend, M=200):
+    data = synthetic_mnist(M * N, seed=3)
+    val = synthetic_mnist(128, seed=4)
+    shards = [data.select(torch.arange(i * M, (i + 1) * M)) for i in range(N)]
+    pconf = {"problem_name": "t", "train_batch_size": 32, "val_batch_size": 64, "metrics": METRICS,
+             "metrics_config": {"evaluate_frequency": 3}, "optimizer_config": conf}
+    torch.manual_seed(5)
+    base = MNISTConvNet(3, 5, 64)
+    return DistMNISTProblem(graph, base, torch.nn.NLLLoss(), shards, val, ctx.device, pconf, ctx=ctx,
+                            backend=backend, seed=11)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cuda", type=int, default=0)
+    ap.add_argument("--nodes", type=int, default=6)
+    ap.add_argument("--graph", default="cycle")
+    args = ap.parse_args()
+    ctx = DistContext.from_env(use_cuda=bool(args.cuda))
+    N = args.nodes
+    G = {"cycle": nx.cycle_graph(N), "wheel": nx.wheel_graph(N), "complete": nx.complete_graph(N)}[args.graph]
+    backend = "fused" if args.cuda else "torch"
+    ok = True
+    for alg, conf in CONFS.items():
+        pr = build(ctx, N, G, conf, backend)
+        opt = build_optimizer(pr, ctx.device, copy.deepcopy(conf))
+        opt.train()
+        theta = pr.gather_rows(pr.arena.theta).cpu()
+        vl = pr.metrics["validation_loss"][-1]
+        if ctx.is_main:
+            solo = DistContext.single(ctx.device)
+            pr1 = build(solo, N, G, conf, backend)
+            opt1 = build_optimizer(pr1, solo.device, copy.deepcopy(conf))
+            opt1.train()
+            ref = pr1.arena.theta.cpu()
+            bad = ((theta - ref).abs() > 2e-5 + 2e-3 * ref.abs()).float().mean().item()
+            rel = ((theta - ref).norm() / ref.norm()).item()
+            vd = (vl - pr1.metrics["validation_loss"][-1]).abs().max().item()
+            good = bad < 5e-3 and rel < 1e-2 and vd < 1e-3
+            print(f"[dist] {alg} world={ctx.world_size} graph={args.graph} bad={bad:.2e} rel={rel:.2e} "
+                  f"val_diff={vd:.2e} {'OK' if good else 'MISMATCH'}", flush=True)
+            ok = ok and good
+        ctx.barrier()
+    if ctx.is_main:
+        print("DIST_RESULT", "PASS" if ok else "FAIL", flush=True)
+    if torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
