@@ -42,3 +42,12 @@ def mnist_kernel_supports(spec, batch_size: int) -> bool:
     """Shapes the hand-written MNIST kernel is instantiated for."""
     return (spec.in_hw == 28 and spec.num_classes == 10 and spec.kernel_size == 5
             and spec.num_filters == 3 and spec.linear_width == 64 and 1 <= batch_size <= 4096)
+
+
+def mlp_kernel_supports(spec, base_loss) -> bool:
+    """Shapes/losses the tcgen05 MLP kernel (csrc/mlp_tc.cu) is instantiated for."""
+    try:
+        from .mlp_fused import supports
+    except Exception:  # noqa: BLE001
+        return False
+    return supports(spec, base_loss)

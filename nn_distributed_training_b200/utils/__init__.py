@@ -1,0 +1,1 @@
+from . import graph_generation  # noqa: F401

@@ -1,0 +1,155 @@
+"""End-to-end runner tests on CPU with small configs (plumbing / API / output-layout parity)."""
+import copy
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+from nn_distributed_training_b200.experiments import dist_mnist_ex, dist_online_dense_ex, dist_dense_ex, dist_mnist_scaling
+from nn_distributed_training_b200.utils.config import ConfigError, load_experiment, validate_optimizer
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXP = os.path.join(ROOT, "experiments")
+
+
+def _write(tmp_path, name, conf):
+    p = os.path.join(tmp_path, name)
+    with open(p, "w") as f:
+        yaml.safe_dump(conf, f)
+    return p
+
+
+def _load(name):
+    with open(os.path.join(EXP, name)) as f:
+        return yaml.safe_load(f)
+
+
+def test_all_shipped_yamls_validate():
+    kinds = {"dist_mnist_PAPER.yaml": "mnist", "dist_mnist_anim.yaml": "mnist", "dist_mnist_template.yaml": "mnist",
+             "dist_mnist_8gpu.yaml": "mnist", "dist_mnist_scaling.yaml": "mnist_scaling",
+             "dist_online_dense_PAPER.yaml": "online_density", "dist_online_dense_anim.yaml": "online_density",
+             "dist_online_dense_synthetic.yaml": "online_density", "dist_dense_v2.yaml": "density"}
+    for name, kind in kinds.items():
+        conf = load_experiment(os.path.join(EXP, name), kind)
+        assert conf["experiment"]["name"]
+
+
+def test_config_errors_are_explicit():
+    with pytest.raises(ConfigError, match="alg_name"):
+        validate_optimizer({"outer_iterations": 3})
+    with pytest.raises(ConfigError, match="rho_init"):
+        validate_optimizer({"alg_name": "dinno", "outer_iterations": 3, "primal_iterations": 1, "primal_lr_start": 1e-3})
+    # the README's legacy names still load
+    c = validate_optimizer({"alg_name": "cadmm", "rho": 0.5, "primal_lr": 1e-3, "outer_iterations": 3, "primal_iterations": 1})
+    assert c["alg_name"] == "dinno" and c["rho_init"] == 0.5 and c["lr_decay_type"] == "constant"
+
+
+def test_mnist_template_runs_and_writes_reference_layout(tmp_path, monkeypatch):
+    """BASELINE config 1: dist_mnist_ex.py + dist_mnist_template.yaml, DSGD, 2 nodes, CPU."""
+    import nn_distributed_training_b200.data.mnist as M
+    monkeypatch.setattr(M, "load_mnist", lambda d, train, **k: (M.synthetic_mnist(512 if train else 128, seed=int(train)), "synthetic"))
+    monkeypatch.setattr(dist_mnist_ex, "load_mnist", M.load_mnist)
+    conf = _load("dist_mnist_template.yaml")
+    conf["experiment"].update(output_metadir=str(tmp_path), writeout=True)
+    oc = conf["problem_configs"]["problem1"]["optimizer_config"]
+    oc["outer_iterations"] = 6
+    conf["problem_configs"]["problem1"]["metrics_config"]["evaluate_frequency"] = 2
+    conf["problem_configs"]["problem2"] = copy.deepcopy(conf["problem_configs"]["problem1"])
+    conf["problem_configs"]["problem2"].update(problem_name="dinno")
+    conf["problem_configs"]["problem2"]["optimizer_config"] = {
+        "alg_name": "dinno", "rho_init": 0.5, "rho_scaling": 1.0003, "outer_iterations": 4, "primal_iterations": 2,
+        "primal_optimizer": "adam", "persistant_primal_opt": False, "primal_lr_start": 0.005,
+        "primal_lr_finish": 0.0005, "lr_decay_type": "log", "profile": False,
+        "checkpoint_every": 2}
+    dist_mnist_ex.experiment(_write(str(tmp_path), "c.yaml", conf))
+    outs = glob.glob(os.path.join(str(tmp_path), "*_dist_mnist_template"))
+    assert len(outs) == 1
+    files = set(os.listdir(outs[0]))
+    assert {"graph.gpickle", "dsgd_results.pt", "dinno_results.pt"} <= files
+    assert any(f.endswith(".yaml") for f in files)
+    assert "dinno_ckpt_rank0.pt" in files
+    res = torch.load(os.path.join(outs[0], "dsgd_results.pt"), weights_only=False)
+    assert set(res) == {"forward_pass_count", "validation_loss", "consensus_error", "top1_accuracy", "current_epoch"}
+    assert len(res["validation_loss"]) == 4          # rounds 0, 2, 4 and the last (5)
+    assert res["validation_loss"][0].shape == (2,)
+    d_all, d_mean = res["consensus_error"][0]
+    assert d_all.shape == (2, 2) and d_mean.shape == (2, 1)
+    assert res["forward_pass_count"] == [0, 128, 256, 320]
+    from nn_distributed_training_b200.experiments.common import read_gpickle
+    assert read_gpickle(os.path.join(outs[0], "graph.gpickle")).number_of_nodes() == 2
+
+
+@pytest.fixture(scope="module")
+def synthetic_dir(tmp_path_factory):
+    from nn_distributed_training_b200.floorplans.synthetic import write_dataset
+    d = str(tmp_path_factory.mktemp("floor"))
+    write_dataset(d, n_paths=4, seed=0)
+    return d
+
+
+def _small_density_conf(name, synthetic_dir, tmp_path):
+    conf = _load(name)
+    e = conf["experiment"]
+    e.update(output_metadir=str(tmp_path), use_cuda=False)
+    e["data"].update(data_dir=synthetic_dir, num_beams=8, beam_samps=10, collision_samps=20, spline_res=4,
+                     num_validation_scans=20, border_width=8)
+    e["model"]["shape"] = [2, 32, 16, 1]
+    e["individual_training"].update(train_solo=True, train_batch_size=500, val_batch_size=500, epochs=1)
+    return conf
+
+
+def test_online_density_runner_dynamic_graph(tmp_path, synthetic_dir):
+    conf = _small_density_conf("dist_online_dense_PAPER.yaml", synthetic_dir, tmp_path)
+    conf["experiment"]["data"].update(num_scans_in_window=10, num_nodes=3)
+    for k, pc in conf["problem_configs"].items():
+        pc.update(train_batch_size=300, val_batch_size=400, comm_radius=300.0)
+        pc["metrics"] = pc["metrics"] + ["current_position", "current_graph"]
+        pc["metrics_config"].update(evaluate_frequency=3)
+        pc["optimizer_config"]["outer_iterations"] = 7
+    dist_online_dense_ex.experiment(_write(str(tmp_path), "o.yaml", conf))
+    out = glob.glob(os.path.join(str(tmp_path), "*_dist_online_dense_PAPER"))[0]
+    files = set(os.listdir(out))
+    assert {"solo_results.pt", "dinno_log_results.pt", "dsgt_results.pt", "dsgd_results.pt",
+            "dinno_log_models.pt", "dsgt_models.pt", "dsgd_models.pt"} <= files
+    res = torch.load(os.path.join(out, "dinno_log_results.pt"), weights_only=False)
+    assert res["mesh_inputs"].shape[1] == 2
+    assert len(res["mesh_grid_density"]) == 1                      # mesh_only_at_end
+    assert res["mesh_grid_density"][0].shape == (3, res["mesh_inputs"].shape[0], 1)
+    assert len(res["validation_loss"]) == 3 and res["validation_loss"][0].shape == (3,)
+    pos = np.stack(res["current_position"])
+    assert pos.shape == (3, 3, 2) and not np.allclose(pos[0], pos[-1])   # robots moved: windows advanced
+    assert res["train_loss_moving_average"][-1].min() > 0
+    models = torch.load(os.path.join(out, "dinno_log_models.pt"), weights_only=False)
+    assert set(models) == {0, 1, 2} and "seq.0.linear.weight" in models[0]
+
+
+def test_offline_density_runner(tmp_path, synthetic_dir):
+    conf = _small_density_conf("dist_dense_v2.yaml", synthetic_dir, tmp_path)
+    conf["experiment"]["graph"].update(num_nodes=3, p=0.9)
+    conf["experiment"]["individual_training"]["train_solo"] = False
+    pc = conf["problem_configs"]["problem1"]
+    pc.update(train_batch_size=300, val_batch_size=400)
+    pc["metrics_config"]["evaluate_frequency"] = 2
+    pc["optimizer_config"].update(outer_iterations=4, primal_iterations=2)
+    dist_dense_ex.experiment(_write(str(tmp_path), "d.yaml", conf))
+    out = glob.glob(os.path.join(str(tmp_path), "*_dist_dense_v2"))[0]
+    res = torch.load(os.path.join(out, "dinno_results.pt"), weights_only=False)
+    assert res["consensus_error"][0].shape == (3, 3)                # offline stores the pairwise matrix only
+    assert len(res["mesh_grid_density"]) == 3
+
+
+def test_scaling_runner(tmp_path, monkeypatch):
+    import nn_distributed_training_b200.data.mnist as M
+    monkeypatch.setattr(dist_mnist_scaling, "load_mnist",
+                        lambda d, train, **k: (M.synthetic_mnist(600 if train else 100, seed=int(train)), "synthetic"))
+    conf = _load("dist_mnist_scaling.yaml")
+    conf["experiment"].update(output_metadir=str(tmp_path), use_cuda=False, seed=1)
+    conf["experiment"]["scaling"].update(min_N=4, max_N=6, num_trials=2, target_fied=1.0)
+    conf["problem"]["optimizer_config"].update(outer_iterations=3)
+    conf["problem"]["metrics_config"]["evaluate_frequency"] = 2
+    dist_mnist_scaling.experiment(_write(str(tmp_path), "s.yaml", conf))
+    out = glob.glob(os.path.join(str(tmp_path), "*_scaling_dinno_const_fied"))[0]
+    assert {"0.gpickle", "1.gpickle", "0_results.pt", "1_results.pt"} <= set(os.listdir(out))
