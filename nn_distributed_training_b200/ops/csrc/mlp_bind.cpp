@@ -1,3 +1,53 @@
+// Bindings of the tcgen05 MLP kernels (mlp_tc.cu).
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
 #include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include "mlp.h"
+
 namespace py = pybind11;
-void bind_mlp(py::module& m) { (void)m; }
+using namespace nndt;
+
+namespace {
+template <typename P> P* ptr(const py::dict& d, const char* k) {
+  if (!d.contains(k) || d[k].is_none()) return nullptr;
+  return reinterpret_cast<P*>(d[k].cast<uint64_t>());
+}
+int geti(const py::dict& d, const char* k, int dflt = 0) { return d.contains(k) ? d[k].cast<int>() : dflt; }
+double getf(const py::dict& d, const char* k, double dflt = 0) { return d.contains(k) ? d[k].cast<double>() : dflt; }
+void check(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+struct MlpOp {
+  mlp::Args a{};
+  int fwd_ctas = 1, train_ctas = 1;
+  explicit MlpOp(const py::dict& d) { update(d); }
+  void update(const py::dict& d) {
+    a.theta = ptr<const float>(d, "theta"); a.n_pad = geti(d, "n_pad"); a.L = geti(d, "L");
+    auto off = d["off"].cast<std::vector<int>>();
+    for (int i = 0; i < 10; ++i) a.off[i] = off.at(i);
+    a.d_in = geti(d, "d_in"); a.h1 = geti(d, "h1");
+    a.first_act = geti(d, "first_act"); a.last_act = geti(d, "last_act"); a.loss = geti(d, "loss");
+    a.scale = (float)getf(d, "scale", 1.0);
+    a.x = ptr<const float>(d, "x"); a.y = ptr<const float>(d, "y");
+    a.n_rows = geti(d, "n_rows"); a.out = ptr<float>(d, "out");
+    a.direct = geti(d, "direct"); a.batch = geti(d, "batch"); a.seed = geti(d, "seed"); a.node0 = geti(d, "node0");
+    a.shard_off = ptr<const int>(d, "shard_off"); a.shard_len = ptr<const int>(d, "shard_len");
+    a.calls = ptr<const int>(d, "calls"); a.win_table = ptr<const int64_t>(d, "win_table");
+    a.grad_part = ptr<float>(d, "grad_part"); a.loss_part = ptr<float>(d, "loss_part"); a.S = geti(d, "S", 1);
+    fwd_ctas = geti(d, "fwd_ctas", 1); train_ctas = geti(d, "train_ctas", 1);
+  }
+  void forward() { check(mlp::launch_forward(a, fwd_ctas, at::cuda::getCurrentCUDAStream().stream()), "mlp_forward"); }
+  void train() { check(mlp::launch_train(a, train_ctas, at::cuda::getCurrentCUDAStream().stream()), "mlp_train"); }
+};
+}  // namespace
+
+void bind_mlp(py::module& m) {
+  py::class_<MlpOp>(m, "MlpOp")
+      .def(py::init<const py::dict&>())
+      .def("update", &MlpOp::update)
+      .def("forward", &MlpOp::forward)
+      .def("train", &MlpOp::train);
+}
