@@ -10,6 +10,7 @@
 // problems/dist_online_dense_problem.py:117-127 (5 eager GEMMs + elementwise kernels per pass).
 #include "common.cuh"
 #include "mlp.h"
+#include "sampler.cuh"
 #include "umma.cuh"
 
 namespace nndt {
@@ -210,9 +211,404 @@ cudaError_t launch_forward(const Args& a, int ctas_per_node, cudaStream_t st) {
   }
 }
 
+// =====================================================================================
+// Training: forward + backward of one minibatch per node, gradients to per-CTA partial rows.
+//
+// Backward GEMMs reuse the forward operand tiles through MN-major descriptors:
+//   dH_{l-1}[128 x K_in] = dZ_l[128 x 64] (K-major A, K = out features) . W_l (MN-major B: N = in features,
+//                          K = the 64 weight rows)
+//   dW_l accumulators    = dZ_l^T . H_{l-1}: both operands MN-major with K = the 128 batch rows, fp32
+//                          accumulation kept in TMEM across all tiles of a node and flushed once.
+// TMEM map (512 columns): [0,256) scratch (forward D / dH), [256,320) dW3, [320,384) dW2,
+// [384,512) dW1^T (two 128-lane blocks of the 256 input features x 64 outputs).
+// =====================================================================================
+constexpr int kWinMax = 64;                           // max windows per period of the online stream
+constexpr int kWinTableLen = 2 + (kWinMax + 1) + 2 * kWinMax;
+
+template <int H1>
+struct TrainSmem {
+  alignas(1024) uint8_t w1[(H1 / 64) * W_SLAB];
+  alignas(1024) uint8_t w2[W_SLAB];
+  alignas(1024) uint8_t w3[W_SLAB];
+  alignas(1024) uint8_t h1[(H1 / 64) * ACT_SLAB];
+  alignas(1024) uint8_t dz[ACT_SLAB];       // dZ of the layer being back-propagated (the slab after it is the
+  alignas(1024) uint8_t h2[ACT_SLAB];       //  don't-care second M atom of the dW GEMMs)
+  alignas(1024) uint8_t h3[ACT_SLAB];
+  float w0[H1 * MAX_DIN];
+  float b0[H1];
+  float b1[HID], b2[HID], b3[HID], w4[HID];
+  float b4;
+  // per-node gradient accumulators of the CUDA-core layers
+  float g_w0[H1 * MAX_DIN];
+  float g_b0[H1];
+  float g_b1[HID], g_b2[HID], g_b3[HID], g_w4[HID];
+  float g_b4;
+  float loss_acc;
+  float xs[TILE * MAX_DIN];
+  float ys[TILE];
+  float part[TILE];
+  float dz5[TILE];
+  int ridx[TILE];
+  alignas(8) uint64_t bar;
+  uint32_t tmem_base;
+};
+
+// column sums over the 32 lanes of a warp of 32 per-lane values: 31 shuffles; lane j returns column j
+NNDT_DEVINL float colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool hi = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = hi ? v[i] : v[i + o];
+      const float keep = hi ? v[i + o] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
+
+// dH[128 x N] = dZ[128 x 64] . W  (A K-major, B MN-major with `n_atoms` 64-wide atoms `W_SLAB` apart)
+template <int N>
+NNDT_DEVINL void gemm_dh(uint32_t tmem_d, const uint8_t* dz, const uint8_t* w) {
+  constexpr uint32_t idesc = make_idesc(128, N, false, true);
+  const uint32_t a0 = smem_u32(dz), b0 = smem_u32(w);
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    mma_bf16(tmem_d, desc_kmajor(a0, k), desc_mnmajor(b0, k, W_SLAB), idesc, k != 0);
+}
+// acc[128 x 64] (+)= A^T . B over the 128 tile rows; A, B MN-major slabs (A: 2 atoms `a_lbo` apart)
+NNDT_DEVINL void gemm_dw(uint32_t tmem_d, const uint8_t* a_slab, uint32_t a_lbo, const uint8_t* b_slab, bool accumulate) {
+  constexpr uint32_t idesc = make_idesc(128, 64, true, true);
+  const uint32_t a0 = smem_u32(a_slab), b0 = smem_u32(b_slab);
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    mma_bf16(tmem_d, desc_mnmajor(a0, k, a_lbo), desc_mnmajor(b0, k, ACT_SLAB), idesc, accumulate || k != 0);
+}
+
+template <int H1>
+__global__ void __launch_bounds__(NT, 1) mlp_train_kernel(const Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  TrainSmem<H1>& sm = *reinterpret_cast<TrainSmem<H1>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int colhalf = warp >> 2, row = (warp & 3) * 32 + lane;
+  const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+
+  if (warp == 0) tmem_alloc(&sm.tmem_base, 512);
+  if (tid == 32) { mbar_init(&sm.bar, 1); mbar_init_fence(); }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tm = sm.tmem_base;
+  const uint32_t T_SCR = tm, T_DW3 = tm + 256, T_DW2 = tm + 320, T_DW1 = tm + 384;
+  uint32_t phase = 0;
+
+  // ---- static work partition: items (node, tile) in node-major order -------------------------
+  const int Tmax = (a.batch + TILE - 1) / TILE;
+  const int I = a.L * Tmax, G = gridDim.x, c = blockIdx.x;
+  const int it0 = (int)(((long long)c * I) / G), it1 = (int)(((long long)(c + 1) * I) / G);
+
+  int cur = -1;          // node whose weights / accumulators are live
+  bool have_acc = false;
+  uint32_t bs = 0, start = 0, key = 0, m = 0;
+  int shard_off = 0;
+  long long first_draw = 0;            // online sliding-window mode: index of the batch's first draw
+  const long long* wt = nullptr;       // [K, P, cum[0..KMAX], lb[KMAX], ub[KMAX]] of the current node
+
+  for (int it = it0; it <= it1; ++it) {
+    const int l = (it < it1) ? it / Tmax : -1;
+    if (l != cur) {
+      // ---------------- flush the finished node segment ---------------------------------------
+      if (cur >= 0) {
+        // slot of this CTA among the CTAs that cover node `cur`
+        const long long first_item = (long long)cur * Tmax;
+        int cf = (int)((first_item * G) / I);
+        while ((long long)(cf + 1) * I / G <= first_item) ++cf;
+        while ((long long)cf * I / G > first_item) --cf;
+        const int slot = c - cf;
+        float* gp = a.grad_part + ((size_t)cur * a.S + slot) * a.n_pad;
+        fence_after_sync();
+        float v[32];
+        // dW3, dW2: lanes 0..63 = output feature n, columns = input feature k
+        for (int q = 0; q < 2; ++q) {
+          const uint32_t base = q == 0 ? T_DW3 : T_DW2;
+          const int off = q == 0 ? a.off[6] : a.off[4];
+          tmem_ld32(base + lane_addr + colhalf * 32, v);
+          if (row < HID) {
+            float4* dst = reinterpret_cast<float4*>(gp + off + row * HID + colhalf * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              dst[i] = have_acc ? make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        // dW1^T blocks: lane = input feature k (within the 128-block), column = output feature n
+        for (int blk = 0; blk < (H1 + 127) / 128; ++blk) {
+          tmem_ld32(T_DW1 + blk * 64 + lane_addr + colhalf * 32, v);
+          const int k = blk * 128 + row;
+          if (k < H1) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) gp[a.off[2] + (colhalf * 32 + i) * H1 + k] = have_acc ? v[i] : 0.f;
+          }
+        }
+        fence_before_sync();
+        for (int o = tid; o < H1 * a.d_in; o += NT) gp[a.off[0] + o] = sm.g_w0[o];
+        for (int o = tid; o < H1; o += NT) gp[a.off[1] + o] = sm.g_b0[o];
+        if (tid < HID) {
+          gp[a.off[3] + tid] = sm.g_b1[tid];
+          gp[a.off[5] + tid] = sm.g_b2[tid];
+          gp[a.off[7] + tid] = sm.g_b3[tid];
+          gp[a.off[8] + tid] = sm.g_w4[tid];
+        }
+        if (tid == 0) { gp[a.off[9]] = sm.g_b4; a.loss_part[cur * a.S + slot] = sm.loss_acc; }
+        __syncthreads();
+      }
+      if (l < 0) break;
+      // ---------------- set up the next node ----------------------------------------------------
+      cur = l;
+      have_acc = false;
+      const float* th = a.theta + (size_t)l * a.n_pad;
+      stage_all_weights<H1>(sm, a, th, tid);
+      for (int o = tid; o < H1 * MAX_DIN; o += NT) sm.g_w0[o] = 0.f;
+      for (int o = tid; o < H1; o += NT) sm.g_b0[o] = 0.f;
+      if (tid < HID) { sm.g_b1[tid] = 0.f; sm.g_b2[tid] = 0.f; sm.g_b3[tid] = 0.f; sm.g_w4[tid] = 0.f; }
+      if (tid == 0) { sm.g_b4 = 0.f; sm.loss_acc = 0.f; }
+      if (a.direct) {
+        bs = (uint32_t)a.batch;
+      } else {
+        m = (uint32_t)a.shard_len[l];
+        shard_off = a.shard_off[l];
+        const BatchLoc loc = locate_batch((uint32_t)a.calls[l], m, (uint32_t)a.batch);
+        bs = loc.size; start = loc.start;
+        key = mix_key((uint32_t)a.seed, (uint32_t)(a.node0 + l), loc.epoch);
+        if (a.win_table != nullptr) {
+          wt = reinterpret_cast<const long long*>(a.win_table) + (size_t)l * kWinTableLen;
+          first_draw = (long long)loc.epoch * m + loc.start;
+        }
+      }
+      fence_async_smem();
+      __syncthreads();
+    }
+    const int tile = it - l * Tmax;
+    const uint32_t t0 = (uint32_t)tile * TILE;
+    if (t0 >= bs) continue;                              // partial batch: nothing in this tile
+    const float inv_bs = 1.f / (float)bs;
+
+    // ---- gather the tile's rows -------------------------------------------------------------------
+    if (tid < TILE) {
+      const uint32_t t = t0 + tid;
+      int idx = -1;
+      if (t < bs) {
+        if (a.direct) {
+          idx = (int)(l * a.batch + t);
+        } else if (wt != nullptr) {
+          // sliding window stream (floorplans/lidar/lidar.py:397-424 as index arithmetic)
+          const long long K = wt[0], P = wt[1];
+          const long long d = first_draw + t, q = d / P, r = d - q * P;
+          int w = 0;
+          while (w + 1 < K && wt[2 + w + 1] <= r) ++w;
+          const long long lb = wt[2 + kWinMax + 1 + w], ub = wt[2 + kWinMax + 1 + kWinMax + w];
+          const uint32_t wkey = mix_key((uint32_t)a.seed, (uint32_t)(a.node0 + l), (uint32_t)(q * K + w));
+          idx = shard_off + (int)lb + (int)feistel_permute((uint32_t)(r - wt[2 + w]), (uint32_t)(ub - lb), wkey);
+        } else {
+          idx = shard_off + (int)feistel_permute(start + t, m, key);
+        }
+      }
+      sm.ridx[tid] = idx;
+      sm.ys[tid] = idx >= 0 ? a.y[idx] : 0.f;
+    }
+    __syncthreads();
+    for (int o = tid; o < TILE * a.d_in; o += NT) {
+      const int r = o / a.d_in, d = o - r * a.d_in;
+      const int idx = sm.ridx[r];
+      sm.xs[r * MAX_DIN + d] = idx >= 0 ? a.x[(size_t)idx * a.d_in + d] : 0.f;
+    }
+    __syncthreads();
+    first_layer<H1>(sm, a, tid);
+    fence_async_smem();
+    __syncthreads();
+
+    float v[32];
+    // ======================= forward ===============================================================
+    if (tid == 0) { fence_after_sync(); gemm_kmajor(T_SCR, sm.h1, sm.w1, H1 / 64, false); commit(&sm.bar); }
+    mbar_wait(&sm.bar, phase); phase ^= 1;
+    fence_after_sync();
+    hidden_epilogue(T_SCR, sm.b1, sm.h2, warp, lane, v);
+    fence_before_sync(); fence_async_smem();
+    __syncthreads();
+    if (tid == 0) { fence_after_sync(); gemm_kmajor(T_SCR, sm.h2, sm.w2, 1, false); commit(&sm.bar); }
+    mbar_wait(&sm.bar, phase); phase ^= 1;
+    fence_after_sync();
+    hidden_epilogue(T_SCR, sm.b2, sm.h3, warp, lane, v);
+    fence_before_sync(); fence_async_smem();
+    __syncthreads();
+    if (tid == 0) { fence_after_sync(); gemm_kmajor(T_SCR, sm.h3, sm.w3, 1, false); commit(&sm.bar); }
+    mbar_wait(&sm.bar, phase); phase ^= 1;
+    fence_after_sync();
+    hidden_epilogue(T_SCR, sm.b3, nullptr, warp, lane, v);     // v = h4[row][colhalf*32 ..]
+    fence_before_sync();
+    // ---- output layer, loss, dL/dz5 --------------------------------------------------------------------
+    {
+      float dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) dot = fmaf(v[i], sm.w4[colhalf * 32 + i], dot);
+      if (colhalf == 1) sm.part[row] = dot;
+      __syncthreads();
+      if (colhalf == 0) {
+        const bool valid = sm.ridx[row] >= 0;
+        const float z = dot + sm.part[row] + sm.b4;
+        const float y = sm.ys[row];
+        float p = z, dpdz = 1.f;
+        if (a.last_act == kLastSigmoid) { p = 1.f / (1.f + __expf(-z)); dpdz = p * (1.f - p); }
+        float loss, g;
+        if (a.loss == kLossBCE) {
+          loss = -(y * fmaxf(__logf(p), -100.f) + (1.f - y) * fmaxf(__logf(1.f - p), -100.f));
+          g = (a.last_act == kLastSigmoid) ? (p - y) : (p - y) / fmaxf(p * (1.f - p), 1e-12f);
+        } else if (a.loss == kLossMSE) {
+          loss = (p - y) * (p - y); g = 2.f * (p - y) * dpdz;
+        } else {
+          loss = fabsf(p - y); g = (p > y ? 1.f : (p < y ? -1.f : 0.f)) * dpdz;
+        }
+        sm.dz5[row] = valid ? g * inv_bs : 0.f;
+        float lsum = warp_sum(valid ? loss * inv_bs : 0.f);
+        float gsum = warp_sum(valid ? g * inv_bs : 0.f);
+        if (lane == 0) { atomicAdd(&sm.loss_acc, lsum); atomicAdd(&sm.g_b4, gsum); }
+      }
+      __syncthreads();
+    }
+    // ======================= backward ================================================================
+    {
+      // layer 5 -> dz4 = dz5 * w4 * relu'(h4);  dW4 += dz5 * h4;  db3 += colsum(dz4)
+      const float d5 = sm.dz5[row];
+      float t1[32], t2[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        t1[i] = d5 * v[i];                                             // dW4 contribution
+        v[i] = v[i] > 0.f ? d5 * sm.w4[colhalf * 32 + i] : 0.f;          // dz4
+        t2[i] = v[i];
+      }
+#pragma unroll
+      for (int cch = 0; cch < 4; ++cch)
+        *reinterpret_cast<uint4*>(sm.dz + swz_chunk_off(row, colhalf * 4 + cch)) = pack_bf16x8(v + 8 * cch);
+      const float s1 = colsum32(t1, lane), s2 = colsum32(t2, lane);
+      atomicAdd(&sm.g_w4[colhalf * 32 + lane], s1);
+      atomicAdd(&sm.g_b3[colhalf * 32 + lane], s2);
+    }
+    fence_async_smem();
+    __syncthreads();
+    // dh3 = dz4 . W3 ; dW3 += dz4^T . h3
+    if (tid == 0) {
+      fence_after_sync();
+      gemm_dh<64>(T_SCR, sm.dz, sm.w3);
+      gemm_dw(T_DW3, sm.dz, ACT_SLAB, sm.h3, have_acc);
+      commit(&sm.bar);
+    }
+    mbar_wait(&sm.bar, phase); phase ^= 1;
+    fence_after_sync();
+#pragma unroll 1
+    for (int layer = 3; layer >= 2; --layer) {
+      // dz_{layer} = dh_{layer} * relu'(h_{layer});  db_{layer-1} += colsum(dz)
+      const uint8_t* hs = layer == 3 ? sm.h3 : sm.h2;
+      float* gb = layer == 3 ? sm.g_b2 : sm.g_b1;
+      tmem_ld32(T_SCR + lane_addr + colhalf * 32, v);
+      fence_before_sync();
+      float t2[32];
+#pragma unroll
+      for (int cch = 0; cch < 4; ++cch) {
+        const uint4 hv = *reinterpret_cast<const uint4*>(hs + swz_chunk_off(row, colhalf * 4 + cch));
+        const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&hv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int i = cch * 8 + e;
+          v[i] = __bfloat162float(hb[e]) > 0.f ? v[i] : 0.f;
+          t2[i] = v[i];
+        }
+      }
+#pragma unroll
+      for (int cch = 0; cch < 4; ++cch)
+        *reinterpret_cast<uint4*>(sm.dz + swz_chunk_off(row, colhalf * 4 + cch)) = pack_bf16x8(v + 8 * cch);
+      const float s2 = colsum32(t2, lane);
+      atomicAdd(&gb[colhalf * 32 + lane], s2);
+      fence_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        fence_after_sync();
+        if (layer == 3) {
+          gemm_dh<64>(T_SCR, sm.dz, sm.w2);
+          gemm_dw(T_DW2, sm.dz, ACT_SLAB, sm.h2, have_acc);
+        } else {
+          gemm_dh<H1>(T_SCR, sm.dz, sm.w1);
+          // dW1^T[k][n] = h1^T . dz2 : A = h1 (M = 128 input features per MMA), B = dz2
+          for (int blk = 0; blk < (H1 + 127) / 128; ++blk)
+            gemm_dw(T_DW1 + blk * 64, sm.h1 + blk * 2 * ACT_SLAB, ACT_SLAB, sm.dz, have_acc);
+        }
+        commit(&sm.bar);
+      }
+      mbar_wait(&sm.bar, phase); phase ^= 1;
+      fence_after_sync();
+    }
+    // ---- first layer: dz1 = dh1 * act'(z1);  dW0 += dz1^T x;  db0 += colsum(dz1) ---------------------------
+    {
+      float x[MAX_DIN];
+#pragma unroll
+      for (int d = 0; d < MAX_DIN; ++d) x[d] = d < a.d_in ? sm.xs[row * MAX_DIN + d] : 0.f;
+      constexpr int BLK = H1 / 64;            // 32-column blocks per warpgroup
+#pragma unroll 1
+      for (int q = 0; q < BLK; ++q) {
+        const int f0 = (colhalf * BLK + q) * 32;
+        tmem_ld32(T_SCR + lane_addr + f0, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int f = f0 + i;
+          float z = sm.b0[f];
+#pragma unroll
+          for (int d = 0; d < MAX_DIN; ++d) if (d < a.d_in) z = fmaf(x[d], sm.w0[f * a.d_in + d], z);
+          float dact;
+          if (a.first_act == kFirstSinRelu) {
+            float sn, cs;
+            __sincosf(a.scale * z, &sn, &cs);
+            dact = sn > 0.f ? cs * a.scale : 0.f;
+          } else {
+            dact = z > 0.f ? 1.f : 0.f;
+          }
+          v[i] *= dact;
+        }
+        float t[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) t[i] = v[i];
+        atomicAdd(&sm.g_b0[f0 + lane], colsum32(t, lane));
+        for (int d = 0; d < a.d_in; ++d) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) t[i] = v[i] * x[d];
+          atomicAdd(&sm.g_w0[(f0 + lane) * a.d_in + d], colsum32(t, lane));
+        }
+      }
+      fence_before_sync();
+    }
+    have_acc = true;
+    __syncthreads();
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tm, 512);
+}
+
+template <int H1>
+static cudaError_t launch_train_t(const Args& a, int ctas, cudaStream_t st) {
+  const int smem = (int)sizeof(TrainSmem<H1>) + 1024;
+  static cudaError_t attr = cudaFuncSetAttribute(mlp_train_kernel<H1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (attr != cudaSuccess) return attr;
+  mlp_train_kernel<H1><<<dim3(ctas), NT, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_train(const Args& a, int ctas, cudaStream_t st) {
-  (void)a; (void)ctas; (void)st;
-  return cudaErrorNotSupported;
+  if (a.d_in > MAX_DIN) return cudaErrorInvalidValue;
+  switch (a.h1) {
+    case 64: return launch_train_t<64>(a, ctas, st);
+    case 128: return launch_train_t<128>(a, ctas, st);
+    case 256: return launch_train_t<256>(a, ctas, st);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 }  // namespace mlp
