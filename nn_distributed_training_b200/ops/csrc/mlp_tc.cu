@@ -73,13 +73,13 @@ NNDT_DEVINL void stage_all_weights(S& sm, const Args& a, const float* th, int ti
 }
 
 // first layer on CUDA cores: h1[r][f] = relu(sin(scale * z)) or relu(z), z = x[r] . W0[f] + b0[f]
-template <int H1, class S>
+template <int H1, int DIN, class S>
 NNDT_DEVINL void first_layer(S& sm, const Args& a, int tid) {
   const int r = tid & (TILE - 1);
   const int half = tid >> 7;                       // 2 thread groups split the features
-  float x[MAX_DIN];
+  float x[DIN];
 #pragma unroll
-  for (int d = 0; d < MAX_DIN; ++d) x[d] = d < a.d_in ? sm.xs[r * MAX_DIN + d] : 0.f;
+  for (int d = 0; d < DIN; ++d) x[d] = sm.xs[r * MAX_DIN + d];
   constexpr int CH = H1 / 8 / 2;                   // 16-byte chunks per thread
   for (int c = 0; c < CH; ++c) {
     const int chunk = half * CH + c;               // global chunk index along the H1 features
@@ -89,7 +89,7 @@ NNDT_DEVINL void first_layer(S& sm, const Args& a, int tid) {
       const int f = chunk * 8 + e;
       float z = sm.b0[f];
 #pragma unroll
-      for (int d = 0; d < MAX_DIN; ++d) if (d < a.d_in) z = fmaf(x[d], sm.w0[f * a.d_in + d], z);
+      for (int d = 0; d < DIN; ++d) z = fmaf(x[d], sm.w0[f * DIN + d], z);
       if (a.first_act == kFirstSinRelu) z = __sinf(a.scale * z);
       v[e] = fmaxf(z, 0.f);
     }
@@ -124,10 +124,10 @@ NNDT_DEVINL void hidden_epilogue(uint32_t tmem_d, const float* bias, uint8_t* ds
   }
 }
 
-template <int H1>
+template <int H1, int DIN>
 __global__ void __launch_bounds__(NT, 1) mlp_forward_kernel(const Args a) {
-  extern __shared__ uint8_t smem_raw[];
-  FwdSmem<H1>& sm = *reinterpret_cast<FwdSmem<H1>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  FwdSmem<H1>& sm = *reinterpret_cast<FwdSmem<H1>*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int l = blockIdx.y;
   const float* th = a.theta + (size_t)l * a.n_pad;
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_forward_kernel(const Args a) {
       sm.xs[r * MAX_DIN + d] = (row0 + r < a.n_rows) ? a.x[(size_t)(row0 + r) * a.d_in + d] : 0.f;
     }
     __syncthreads();
-    first_layer<H1>(sm, a, tid);
+    first_layer<H1, DIN>(sm, a, tid);
     fence_async_smem();
     __syncthreads();
 
@@ -194,10 +194,11 @@ __global__ void __launch_bounds__(NT, 1) mlp_forward_kernel(const Args a) {
 
 template <int H1>
 static cudaError_t launch_forward_t(const Args& a, int ctas, cudaStream_t st) {
-  const int smem = (int)sizeof(FwdSmem<H1>) + 1024;
-  static cudaError_t attr = cudaFuncSetAttribute(mlp_forward_kernel<H1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int smem = (int)sizeof(FwdSmem<H1>);
+  static cudaError_t attr = cudaFuncSetAttribute(mlp_forward_kernel<H1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (attr != cudaSuccess) return attr;
-  mlp_forward_kernel<H1><<<dim3(ctas, a.L), NT, smem, st>>>(a);
+  if (a.d_in != 2) return cudaErrorInvalidValue;
+  mlp_forward_kernel<H1, 2><<<dim3(ctas, a.L), NT, smem, st>>>(a);
   return cudaGetLastError();
 }
 
@@ -217,10 +218,13 @@ cudaError_t launch_forward(const Args& a, int ctas_per_node, cudaStream_t st) {
 // Backward GEMMs reuse the forward operand tiles through MN-major descriptors:
 //   dH_{l-1}[128 x K_in] = dZ_l[128 x 64] (K-major A, K = out features) . W_l (MN-major B: N = in features,
 //                          K = the 64 weight rows)
-//   dW_l accumulators    = dZ_l^T . H_{l-1}: both operands MN-major with K = the 128 batch rows, fp32
-//                          accumulation kept in TMEM across all tiles of a node and flushed once.
-// TMEM map (512 columns): [0,256) scratch (forward D / dH), [256,320) dW3, [320,384) dW2,
-// [384,512) dW1^T (two 128-lane blocks of the 256 input features x 64 outputs).
+//   dW_l accumulators    = dZ_l^T . H_{l-1}: both operands MN-major with K = the 128 batch rows; fp32
+//                          accumulation stays in TMEM across all tiles of a node and is flushed once.
+//   bias / first-layer grads = dZ^T . [x, 1]: the same trick against a 16-column slab holding the tile's
+//                          inputs and a ones column, so no cross-lane shuffle reductions are needed.
+// TMEM map (columns): [0,128) scratch (forward D / dH) | [128,192) dW3 | [192,256) dW2 |
+//   [256,384) dW1^T (2 blocks of 128 input features x 64) | [384,416) [dW0 | db0] (2 blocks x 16) |
+//   [416,432) db3 | [432,448) db2 | [448,464) db1   (bias sums live in column DIN of their block)
 // =====================================================================================
 constexpr int kWinMax = 64;                           // max windows per period of the online stream
 constexpr int kWinTableLen = 2 + (kWinMax + 1) + 2 * kWinMax;
@@ -230,18 +234,16 @@ struct TrainSmem {
   alignas(1024) uint8_t w1[(H1 / 64) * W_SLAB];
   alignas(1024) uint8_t w2[W_SLAB];
   alignas(1024) uint8_t w3[W_SLAB];
-  alignas(1024) uint8_t h1[(H1 / 64) * ACT_SLAB];
+  alignas(1024) uint8_t h1[(H1 < 128 ? 2 : H1 / 64) * ACT_SLAB];   // h1, later dZ1 (>= 2 slabs: M = 128 A operand)
   alignas(1024) uint8_t dz[ACT_SLAB];       // dZ of the layer being back-propagated (the slab after it is the
   alignas(1024) uint8_t h2[ACT_SLAB];       //  don't-care second M atom of the dW GEMMs)
   alignas(1024) uint8_t h3[ACT_SLAB];
+  alignas(1024) uint8_t xa[ACT_SLAB];       // [x_0..x_{DIN-1}, 1, 0...] per row, 16 valid columns
   float w0[H1 * MAX_DIN];
   float b0[H1];
   float b1[HID], b2[HID], b3[HID], w4[HID];
   float b4;
-  // per-node gradient accumulators of the CUDA-core layers
-  float g_w0[H1 * MAX_DIN];
-  float g_b0[H1];
-  float g_b1[HID], g_b2[HID], g_b3[HID], g_w4[HID];
+  float g_w4[HID];
   float g_b4;
   float loss_acc;
   float xs[TILE * MAX_DIN];
@@ -268,7 +270,7 @@ NNDT_DEVINL float colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
-// dH[128 x N] = dZ[128 x 64] . W  (A K-major, B MN-major with `n_atoms` 64-wide atoms `W_SLAB` apart)
+// dH[128 x N] = dZ[128 x 64] . W  (A K-major; B MN-major: N/64 atoms W_SLAB apart starting at `w`)
 template <int N>
 NNDT_DEVINL void gemm_dh(uint32_t tmem_d, const uint8_t* dz, const uint8_t* w) {
   constexpr uint32_t idesc = make_idesc(128, N, false, true);
@@ -277,22 +279,25 @@ NNDT_DEVINL void gemm_dh(uint32_t tmem_d, const uint8_t* dz, const uint8_t* w) {
   for (int k = 0; k < 4; ++k)
     mma_bf16(tmem_d, desc_kmajor(a0, k), desc_mnmajor(b0, k, W_SLAB), idesc, k != 0);
 }
-// acc[128 x 64] (+)= A^T . B over the 128 tile rows; A, B MN-major slabs (A: 2 atoms `a_lbo` apart)
-NNDT_DEVINL void gemm_dw(uint32_t tmem_d, const uint8_t* a_slab, uint32_t a_lbo, const uint8_t* b_slab, bool accumulate) {
-  constexpr uint32_t idesc = make_idesc(128, 64, true, true);
+// acc[128 x N] (+)= A^T . B over the 128 tile rows; A, B MN-major slabs (A: 2 atoms ACT_SLAB apart)
+template <int N>
+NNDT_DEVINL void gemm_dw(uint32_t tmem_d, const uint8_t* a_slab, const uint8_t* b_slab, bool accumulate) {
+  constexpr uint32_t idesc = make_idesc(128, N, true, true);
   const uint32_t a0 = smem_u32(a_slab), b0 = smem_u32(b_slab);
 #pragma unroll
   for (int k = 0; k < 8; ++k)
-    mma_bf16(tmem_d, desc_mnmajor(a0, k, a_lbo), desc_mnmajor(b0, k, ACT_SLAB), idesc, accumulate || k != 0);
+    mma_bf16(tmem_d, desc_mnmajor(a0, k, ACT_SLAB), desc_mnmajor(b0, k, ACT_SLAB), idesc, accumulate || k != 0);
 }
 
-template <int H1>
+template <int H1, int DIN>
 __global__ void __launch_bounds__(NT, 1) mlp_train_kernel(const Args a) {
-  extern __shared__ uint8_t smem_raw[];
-  TrainSmem<H1>& sm = *reinterpret_cast<TrainSmem<H1>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  TrainSmem<H1>& sm = *reinterpret_cast<TrainSmem<H1>*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int colhalf = warp >> 2, row = (warp & 3) * 32 + lane;
   const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+  constexpr int NBLK1 = (H1 + 127) / 128;       // 128-feature blocks of the first hidden layer
+  constexpr int NH = H1 > 128 ? 128 : H1;        // dH1 is produced NH columns at a time
 
   if (warp == 0) tmem_alloc(&sm.tmem_base, 512);
   if (tid == 32) { mbar_init(&sm.bar, 1); mbar_init_fence(); }
@@ -300,8 +305,10 @@ __global__ void __launch_bounds__(NT, 1) mlp_train_kernel(const Args a) {
   __syncthreads();
   fence_after_sync();
   const uint32_t tm = sm.tmem_base;
-  const uint32_t T_SCR = tm, T_DW3 = tm + 256, T_DW2 = tm + 320, T_DW1 = tm + 384;
+  const uint32_t T_SCR = tm, T_DW3 = tm + 128, T_DW2 = tm + 192, T_DW1 = tm + 256, T_DW0 = tm + 384,
+                 T_B3 = tm + 416, T_B2 = tm + 432, T_B1 = tm + 448;
   uint32_t phase = 0;
+  bool pending = false;        // MMAs of the previous tile still in flight (committed, not yet waited)
 
   // ---- static work partition: items (node, tile) in node-major order -------------------------
   const int Tmax = (a.batch + TILE - 1) / TILE;
@@ -318,31 +325,29 @@ __global__ void __launch_bounds__(NT, 1) mlp_train_kernel(const Args a) {
   for (int it = it0; it <= it1; ++it) {
     const int l = (it < it1) ? it / Tmax : -1;
     if (l != cur) {
+      if (pending) { mbar_wait(&sm.bar, phase); phase ^= 1; pending = false; }
       // ---------------- flush the finished node segment ---------------------------------------
       if (cur >= 0) {
-        // slot of this CTA among the CTAs that cover node `cur`
         const long long first_item = (long long)cur * Tmax;
         int cf = (int)((first_item * G) / I);
         while ((long long)(cf + 1) * I / G <= first_item) ++cf;
         while ((long long)cf * I / G > first_item) --cf;
-        const int slot = c - cf;
+        const int slot = c - cf;       // this CTA's slot among the CTAs that cover node `cur`
         float* gp = a.grad_part + ((size_t)cur * a.S + slot) * a.n_pad;
         fence_after_sync();
         float v[32];
         // dW3, dW2: lanes 0..63 = output feature n, columns = input feature k
         for (int q = 0; q < 2; ++q) {
-          const uint32_t base = q == 0 ? T_DW3 : T_DW2;
-          const int off = q == 0 ? a.off[6] : a.off[4];
-          tmem_ld32(base + lane_addr + colhalf * 32, v);
+          tmem_ld32((q == 0 ? T_DW3 : T_DW2) + lane_addr + colhalf * 32, v);
           if (row < HID) {
-            float4* dst = reinterpret_cast<float4*>(gp + off + row * HID + colhalf * 32);
+            float4* dst = reinterpret_cast<float4*>(gp + (q == 0 ? a.off[6] : a.off[4]) + row * HID + colhalf * 32);
 #pragma unroll
             for (int i = 0; i < 8; ++i)
               dst[i] = have_acc ? make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
         // dW1^T blocks: lane = input feature k (within the 128-block), column = output feature n
-        for (int blk = 0; blk < (H1 + 127) / 128; ++blk) {
+        for (int blk = 0; blk < NBLK1; ++blk) {
           tmem_ld32(T_DW1 + blk * 64 + lane_addr + colhalf * 32, v);
           const int k = blk * 128 + row;
           if (k < H1) {
@@ -350,15 +355,25 @@ __global__ void __launch_bounds__(NT, 1) mlp_train_kernel(const Args a) {
             for (int i = 0; i < 32; ++i) gp[a.off[2] + (colhalf * 32 + i) * H1 + k] = have_acc ? v[i] : 0.f;
           }
         }
-        fence_before_sync();
-        for (int o = tid; o < H1 * a.d_in; o += NT) gp[a.off[0] + o] = sm.g_w0[o];
-        for (int o = tid; o < H1; o += NT) gp[a.off[1] + o] = sm.g_b0[o];
-        if (tid < HID) {
-          gp[a.off[3] + tid] = sm.g_b1[tid];
-          gp[a.off[5] + tid] = sm.g_b2[tid];
-          gp[a.off[7] + tid] = sm.g_b3[tid];
-          gp[a.off[8] + tid] = sm.g_w4[tid];
+        // 16-column blocks: [dW0 | db0] (lane = first-layer feature) and the hidden bias sums (lane = feature)
+        if (colhalf == 0) {
+          float w[16];
+          for (int blk = 0; blk < NBLK1; ++blk) {
+            tmem_ld16(T_DW0 + blk * 16 + lane_addr, w);
+            const int f = blk * 128 + row;
+            if (f < H1) {
+#pragma unroll
+              for (int d = 0; d < DIN; ++d) gp[a.off[0] + f * DIN + d] = have_acc ? w[d] : 0.f;
+              gp[a.off[1] + f] = have_acc ? w[DIN] : 0.f;
+            }
+          }
+          for (int q = 0; q < 3; ++q) {
+            tmem_ld16((q == 0 ? T_B3 : q == 1 ? T_B2 : T_B1) + lane_addr, w);
+            if (row < HID) gp[a.off[q == 0 ? 7 : q == 1 ? 5 : 3] + row] = have_acc ? w[DIN] : 0.f;
+          }
         }
+        fence_before_sync();
+        if (tid < HID) gp[a.off[8] + tid] = sm.g_w4[tid];
         if (tid == 0) { gp[a.off[9]] = sm.g_b4; a.loss_part[cur * a.S + slot] = sm.loss_acc; }
         __syncthreads();
       }
@@ -368,9 +383,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_train_kernel(const Args a) {
       have_acc = false;
       const float* th = a.theta + (size_t)l * a.n_pad;
       stage_all_weights<H1>(sm, a, th, tid);
-      for (int o = tid; o < H1 * MAX_DIN; o += NT) sm.g_w0[o] = 0.f;
-      for (int o = tid; o < H1; o += NT) sm.g_b0[o] = 0.f;
-      if (tid < HID) { sm.g_b1[tid] = 0.f; sm.g_b2[tid] = 0.f; sm.g_b3[tid] = 0.f; sm.g_w4[tid] = 0.f; }
+      if (tid < HID) sm.g_w4[tid] = 0.f;
       if (tid == 0) { sm.g_b4 = 0.f; sm.loss_acc = 0.f; }
       if (a.direct) {
         bs = (uint32_t)a.batch;
@@ -393,13 +406,14 @@ __global__ void __launch_bounds__(NT, 1) mlp_train_kernel(const Args a) {
     if (t0 >= bs) continue;                              // partial batch: nothing in this tile
     const float inv_bs = 1.f / (float)bs;
 
-    // ---- gather the tile's rows -------------------------------------------------------------------
+    // ---- gather the tile's rows (overlaps the previous tile's last MMAs) ---------------------------
+    int my_idx = -1;
+    float my_x[DIN];
     if (tid < TILE) {
       const uint32_t t = t0 + tid;
-      int idx = -1;
       if (t < bs) {
         if (a.direct) {
-          idx = (int)(l * a.batch + t);
+          my_idx = (int)(l * a.batch + t);
         } else if (wt != nullptr) {
           // sliding window stream (floorplans/lidar/lidar.py:397-424 as index arithmetic)
           const long long K = wt[0], P = wt[1];
@@ -408,22 +422,30 @@ __global__ void __launch_bounds__(NT, 1) mlp_train_kernel(const Args a) {
           while (w + 1 < K && wt[2 + w + 1] <= r) ++w;
           const long long lb = wt[2 + kWinMax + 1 + w], ub = wt[2 + kWinMax + 1 + kWinMax + w];
           const uint32_t wkey = mix_key((uint32_t)a.seed, (uint32_t)(a.node0 + l), (uint32_t)(q * K + w));
-          idx = shard_off + (int)lb + (int)feistel_permute((uint32_t)(r - wt[2 + w]), (uint32_t)(ub - lb), wkey);
+          my_idx = shard_off + (int)lb + (int)feistel_permute((uint32_t)(r - wt[2 + w]), (uint32_t)(ub - lb), wkey);
         } else {
-          idx = shard_off + (int)feistel_permute(start + t, m, key);
+          my_idx = shard_off + (int)feistel_permute(start + t, m, key);
         }
       }
-      sm.ridx[tid] = idx;
-      sm.ys[tid] = idx >= 0 ? a.y[idx] : 0.f;
+#pragma unroll
+      for (int d = 0; d < DIN; ++d) my_x[d] = my_idx >= 0 ? a.x[(size_t)my_idx * DIN + d] : 0.f;
+    }
+    const float my_y = (tid < TILE && my_idx >= 0) ? a.y[my_idx] : 0.f;
+    if (pending) { mbar_wait(&sm.bar, phase); phase ^= 1; pending = false; }   // xa / h1 are free again
+    if (tid < TILE) {
+      sm.ridx[tid] = my_idx;
+      sm.ys[tid] = my_y;
+      float xv[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) xv[e] = 0.f;
+#pragma unroll
+      for (int d = 0; d < DIN; ++d) { sm.xs[tid * MAX_DIN + d] = my_x[d]; xv[d] = my_x[d]; }
+      xv[DIN] = my_idx >= 0 ? 1.f : 0.f;
+      *reinterpret_cast<uint4*>(sm.xa + swz_chunk_off(tid, 0)) = pack_bf16x8(xv);
+      *reinterpret_cast<uint4*>(sm.xa + swz_chunk_off(tid, 1)) = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
-    for (int o = tid; o < TILE * a.d_in; o += NT) {
-      const int r = o / a.d_in, d = o - r * a.d_in;
-      const int idx = sm.ridx[r];
-      sm.xs[r * MAX_DIN + d] = idx >= 0 ? a.x[(size_t)idx * a.d_in + d] : 0.f;
-    }
-    __syncthreads();
-    first_layer<H1>(sm, a, tid);
+    first_layer<H1, DIN>(sm, a, tid);
     fence_async_smem();
     __syncthreads();
 
@@ -469,123 +491,128 @@ __global__ void __launch_bounds__(NT, 1) mlp_train_kernel(const Args a) {
           loss = fabsf(p - y); g = (p > y ? 1.f : (p < y ? -1.f : 0.f)) * dpdz;
         }
         sm.dz5[row] = valid ? g * inv_bs : 0.f;
-        float lsum = warp_sum(valid ? loss * inv_bs : 0.f);
-        float gsum = warp_sum(valid ? g * inv_bs : 0.f);
+        const float lsum = warp_sum(valid ? loss * inv_bs : 0.f);
+        const float gsum = warp_sum(valid ? g * inv_bs : 0.f);
         if (lane == 0) { atomicAdd(&sm.loss_acc, lsum); atomicAdd(&sm.g_b4, gsum); }
       }
       __syncthreads();
     }
     // ======================= backward ================================================================
     {
-      // layer 5 -> dz4 = dz5 * w4 * relu'(h4);  dW4 += dz5 * h4;  db3 += colsum(dz4)
+      // layer 5 -> dz4 = dz5 * w4 * relu'(h4);  dW4 += dz5 * h4 (the one remaining shuffle reduction)
       const float d5 = sm.dz5[row];
-      float t1[32], t2[32];
+      float t1[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        t1[i] = d5 * v[i];                                             // dW4 contribution
-        v[i] = v[i] > 0.f ? d5 * sm.w4[colhalf * 32 + i] : 0.f;          // dz4
-        t2[i] = v[i];
+        t1[i] = d5 * v[i];
+        v[i] = v[i] > 0.f ? d5 * sm.w4[colhalf * 32 + i] : 0.f;
       }
 #pragma unroll
       for (int cch = 0; cch < 4; ++cch)
         *reinterpret_cast<uint4*>(sm.dz + swz_chunk_off(row, colhalf * 4 + cch)) = pack_bf16x8(v + 8 * cch);
-      const float s1 = colsum32(t1, lane), s2 = colsum32(t2, lane);
-      atomicAdd(&sm.g_w4[colhalf * 32 + lane], s1);
-      atomicAdd(&sm.g_b3[colhalf * 32 + lane], s2);
+      atomicAdd(&sm.g_w4[colhalf * 32 + lane], colsum32(t1, lane));
     }
     fence_async_smem();
     __syncthreads();
-    // dh3 = dz4 . W3 ; dW3 += dz4^T . h3
+    // dh3 = dz4 . W3 ; dW3 += dz4^T . h3 ; db3 += dz4^T . [x,1]
     if (tid == 0) {
       fence_after_sync();
       gemm_dh<64>(T_SCR, sm.dz, sm.w3);
-      gemm_dw(T_DW3, sm.dz, ACT_SLAB, sm.h3, have_acc);
+      gemm_dw<64>(T_DW3, sm.dz, sm.h3, have_acc);
+      gemm_dw<16>(T_B3, sm.dz, sm.xa, have_acc);
       commit(&sm.bar);
     }
     mbar_wait(&sm.bar, phase); phase ^= 1;
     fence_after_sync();
 #pragma unroll 1
     for (int layer = 3; layer >= 2; --layer) {
-      // dz_{layer} = dh_{layer} * relu'(h_{layer});  db_{layer-1} += colsum(dz)
+      // dz_{layer} = dh_{layer} * relu'(h_{layer})
       const uint8_t* hs = layer == 3 ? sm.h3 : sm.h2;
-      float* gb = layer == 3 ? sm.g_b2 : sm.g_b1;
       tmem_ld32(T_SCR + lane_addr + colhalf * 32, v);
       fence_before_sync();
-      float t2[32];
 #pragma unroll
       for (int cch = 0; cch < 4; ++cch) {
         const uint4 hv = *reinterpret_cast<const uint4*>(hs + swz_chunk_off(row, colhalf * 4 + cch));
         const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&hv);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int i = cch * 8 + e;
-          v[i] = __bfloat162float(hb[e]) > 0.f ? v[i] : 0.f;
-          t2[i] = v[i];
-        }
+        for (int e = 0; e < 8; ++e) v[cch * 8 + e] = __bfloat162float(hb[e]) > 0.f ? v[cch * 8 + e] : 0.f;
       }
 #pragma unroll
       for (int cch = 0; cch < 4; ++cch)
         *reinterpret_cast<uint4*>(sm.dz + swz_chunk_off(row, colhalf * 4 + cch)) = pack_bf16x8(v + 8 * cch);
-      const float s2 = colsum32(t2, lane);
-      atomicAdd(&gb[colhalf * 32 + lane], s2);
       fence_async_smem();
       __syncthreads();
       if (tid == 0) {
         fence_after_sync();
         if (layer == 3) {
           gemm_dh<64>(T_SCR, sm.dz, sm.w2);
-          gemm_dw(T_DW2, sm.dz, ACT_SLAB, sm.h2, have_acc);
+          gemm_dw<64>(T_DW2, sm.dz, sm.h2, have_acc);
+          gemm_dw<16>(T_B2, sm.dz, sm.xa, have_acc);
         } else {
-          gemm_dh<H1>(T_SCR, sm.dz, sm.w1);
+          gemm_dh<NH>(T_SCR, sm.dz, sm.w1);
           // dW1^T[k][n] = h1^T . dz2 : A = h1 (M = 128 input features per MMA), B = dz2
-          for (int blk = 0; blk < (H1 + 127) / 128; ++blk)
-            gemm_dw(T_DW1 + blk * 64, sm.h1 + blk * 2 * ACT_SLAB, ACT_SLAB, sm.dz, have_acc);
+          for (int blk = 0; blk < NBLK1; ++blk)
+            gemm_dw<64>(T_DW1 + blk * 64, sm.h1 + blk * 2 * ACT_SLAB, sm.dz, have_acc);
+          gemm_dw<16>(T_B1, sm.dz, sm.xa, have_acc);
         }
         commit(&sm.bar);
       }
       mbar_wait(&sm.bar, phase); phase ^= 1;
       fence_after_sync();
     }
-    // ---- first layer: dz1 = dh1 * act'(z1);  dW0 += dz1^T x;  db0 += colsum(dz1) ---------------------------
+    // ---- first layer: dz1 = dh1 * act'(z1) -> bf16 slabs over the dead h1 tile;  [dW0|db0] += dz1^T [x,1] ----
     {
-      float x[MAX_DIN];
+      float x[DIN];
 #pragma unroll
-      for (int d = 0; d < MAX_DIN; ++d) x[d] = d < a.d_in ? sm.xs[row * MAX_DIN + d] : 0.f;
-      constexpr int BLK = H1 / 64;            // 32-column blocks per warpgroup
+      for (int d = 0; d < DIN; ++d) x[d] = sm.xs[row * MAX_DIN + d];
 #pragma unroll 1
-      for (int q = 0; q < BLK; ++q) {
-        const int f0 = (colhalf * BLK + q) * 32;
-        tmem_ld32(T_SCR + lane_addr + f0, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int f = f0 + i;
-          float z = sm.b0[f];
-#pragma unroll
-          for (int d = 0; d < MAX_DIN; ++d) if (d < a.d_in) z = fmaf(x[d], sm.w0[f * a.d_in + d], z);
-          float dact;
-          if (a.first_act == kFirstSinRelu) {
-            float sn, cs;
-            __sincosf(a.scale * z, &sn, &cs);
-            dact = sn > 0.f ? cs * a.scale : 0.f;
-          } else {
-            dact = z > 0.f ? 1.f : 0.f;
-          }
-          v[i] *= dact;
+      for (int half = 0; half < (H1 + NH - 1) / NH; ++half) {
+        if (half > 0) {
+          fence_before_sync();
+          __syncthreads();
+          if (tid == 0) { fence_after_sync(); gemm_dh<NH>(T_SCR, sm.dz, sm.w1 + half * (NH / 64) * W_SLAB); commit(&sm.bar); }
+          mbar_wait(&sm.bar, phase); phase ^= 1;
+          fence_after_sync();
         }
-        float t[32];
+#pragma unroll 1
+        for (int q = 0; q < NH / 64; ++q) {
+          const int f0 = half * NH + (q * 2 + colhalf) * 32;     // this thread's 32 features
+          tmem_ld32(T_SCR + lane_addr + (q * 2 + colhalf) * 32, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) t[i] = v[i];
-        atomicAdd(&sm.g_b0[f0 + lane], colsum32(t, lane));
-        for (int d = 0; d < a.d_in; ++d) {
+          for (int i = 0; i < 32; ++i) {
+            const int f = f0 + i;
+            float z = sm.b0[f];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) t[i] = v[i] * x[d];
-          atomicAdd(&sm.g_w0[(f0 + lane) * a.d_in + d], colsum32(t, lane));
+            for (int d = 0; d < DIN; ++d) z = fmaf(x[d], sm.w0[f * DIN + d], z);
+            float dact;
+            if (a.first_act == kFirstSinRelu) {
+              float sn, cs;
+              __sincosf(a.scale * z, &sn, &cs);
+              dact = sn > 0.f ? cs * a.scale : 0.f;
+            } else {
+              dact = z > 0.f ? 1.f : 0.f;
+            }
+            v[i] *= dact;
+          }
+          const int chunk0 = (f0 & 63) >> 3;
+          uint8_t* slab = sm.h1 + (f0 >> 6) * ACT_SLAB;
+#pragma unroll
+          for (int cch = 0; cch < 4; ++cch)
+            *reinterpret_cast<uint4*>(slab + swz_chunk_off(row, chunk0 + cch)) = pack_bf16x8(v + 8 * cch);
         }
       }
       fence_before_sync();
+      fence_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        fence_after_sync();
+        for (int blk = 0; blk < NBLK1; ++blk)
+          gemm_dw<16>(T_DW0 + blk * 16, sm.h1 + blk * 2 * ACT_SLAB, sm.xa, have_acc);
+        commit(&sm.bar);
+      }
+      pending = true;      // waited for at the top of the next tile / before the flush
     }
     have_acc = true;
-    __syncthreads();
   }
   fence_before_sync();
   __syncthreads();
@@ -594,10 +621,11 @@ __global__ void __launch_bounds__(NT, 1) mlp_train_kernel(const Args a) {
 
 template <int H1>
 static cudaError_t launch_train_t(const Args& a, int ctas, cudaStream_t st) {
-  const int smem = (int)sizeof(TrainSmem<H1>) + 1024;
-  static cudaError_t attr = cudaFuncSetAttribute(mlp_train_kernel<H1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int smem = (int)sizeof(TrainSmem<H1>);
+  static cudaError_t attr = cudaFuncSetAttribute(mlp_train_kernel<H1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (attr != cudaSuccess) return attr;
-  mlp_train_kernel<H1><<<dim3(ctas), NT, smem, st>>>(a);
+  if (a.d_in != 2) return cudaErrorInvalidValue;
+  mlp_train_kernel<H1, 2><<<dim3(ctas), NT, smem, st>>>(a);
   return cudaGetLastError();
 }
 

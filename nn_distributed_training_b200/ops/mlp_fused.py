@@ -15,7 +15,7 @@ TRAIN_KERNEL_READY = True
 
 def shape_supported(spec: MLPSpec) -> bool:
     s = spec.shape
-    return (len(s) == 6 and s[0] <= 4 and s[1] in (64, 128, 256) and tuple(s[2:5]) == (64, 64, 64) and s[5] == 1
+    return (len(s) == 6 and s[0] == 2 and s[1] in (64, 128, 256) and tuple(s[2:5]) == (64, 64, 64) and s[5] == 1
             and spec.first in FIRST and spec.hidden == "relu" and spec.last in LAST)
 
 
