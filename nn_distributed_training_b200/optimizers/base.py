@@ -119,6 +119,7 @@ class ConsensusOptimizer:
     def train(self, profiler=None):
         if self._use_engine():
             self._train_fused(profiler)
+            return
         else:
             self._before_training()
             while self.k < self.oits:

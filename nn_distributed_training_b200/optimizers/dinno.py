@@ -45,7 +45,7 @@ class DiNNO(ConsensusOptimizer):
         super().__init__(ddl_problem, device, conf)
         self.rho = float(conf["rho_init"])
         self.rho_scaling = float(conf["rho_scaling"])
-        self.primal_lr = primal_lr_table(conf)
+        self._primal_lr = None   # materialised lazily: RL runs use outer_iterations ~ 1e7 with a constant rate
         self.pits = int(conf["primal_iterations"])
         self.opt_kind = conf["primal_optimizer"]
         if self.opt_kind not in ("adam", "sgd", "adamw"):
@@ -65,7 +65,19 @@ class DiNNO(ConsensusOptimizer):
         """rho used in round k (rho_init * scaling^(k+1))."""
         return float(self.conf["rho_init"]) * self.rho_scaling ** (k + 1)
 
+    @property
+    def primal_lr(self):
+        if self._primal_lr is None:
+            self._primal_lr = primal_lr_table(self.conf)
+        return self._primal_lr
+
+    @primal_lr.setter
+    def primal_lr(self, table):
+        self._primal_lr = np.asarray(table, dtype=np.float64)
+
     def lr_at(self, k: int) -> float:
+        if self.conf["lr_decay_type"] == "constant" and self._primal_lr is None:
+            return float(self.conf["primal_lr_start"])
         if self.persistent and not self.persistent_follows_schedule:
             return float(self.primal_lr[0])
         return float(self.primal_lr[k])

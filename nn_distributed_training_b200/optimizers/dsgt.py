@@ -24,7 +24,8 @@ class DSGT(ConsensusOptimizer):
 
     def __init__(self, ddl_problem, device, conf):
         super().__init__(ddl_problem, device, conf)
-        self.alpha = float(conf["alpha"])
+        self.alpha = float(conf["alpha"])   # may be replaced by a per-coordinate tensor [n_pad]
+        self.own_tracker_step = bool(conf.get("own_tracker_step", False))
         self.init_grads = bool(conf["init_grads"])
         self.refresh_graph = bool(conf.get("update_graph", True))
         self.y = self.arena.zeros()
@@ -59,7 +60,10 @@ class DSGT(ConsensusOptimizer):
         with torch.no_grad():
             theta_all = pr.gather_rows(a.theta)
             y_all = pr.gather_rows(self.y)
-            a.theta.copy_(ref.dsgt_mix(theta_all, y_all, w_rows, self.alpha))
+            if self.own_tracker_step:   # RL variant: theta_i <- sum_j W_ij theta_j - alpha y_i
+                a.theta.copy_(ref.dsgd_mix(theta_all, w_rows) - self.alpha * self.y)
+            else:
+                a.theta.copy_(ref.dsgt_mix(theta_all, y_all, w_rows, self.alpha))
         pr.compute_grads()
         with torch.no_grad():
             self.y.copy_(ref.dsgt_track(y_all, w_rows, a.grad, self.g))
