@@ -1,0 +1,80 @@
+"""Turn ncu reports in gpurun_out/ into committed summaries under profiles/ (run on the CPU box)."""
+import csv, collections, io, json, os, subprocess, sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "profiles")
+os.makedirs(OUT, exist_ok=True)
+PEAKS = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+
+KEYS = ["gpu__time_duration.sum", "sm__cycles_elapsed.max", "launch__registers_per_thread", "launch__grid_size",
+        "launch__block_size", "launch__shared_mem_per_block_dynamic", "smsp__inst_executed.sum",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_bytes.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"]
+
+
+def ncu_csv(rep, page, extra=()):
+    r = subprocess.run(["ncu", "-i", rep, "--page", page, "--csv", *extra], capture_output=True, text=True)
+    return list(csv.reader(io.StringIO(r.stdout)))
+
+
+def summarize(name, title, notes):
+    rep = os.path.join(ROOT, "gpurun_out", name + ".ncu-rep")
+    if not os.path.exists(rep):
+        return None
+    rows = ncu_csv(rep, "raw")
+    h, units, v = rows[0], rows[1], rows[2]
+    m = dict(zip(h, v)); u = dict(zip(h, units))
+    lines = [f"# {title}", "", f"source: `gpurun_out/{name}.ncu-rep` (ncu --set full --clock-control none --import-source on, 1 launch)", "",
+             f"kernel: `{m.get('Kernel Name', '?')}`", "", "| metric | value | unit |", "|---|---|---|"]
+    for k in KEYS:
+        if k in m:
+            lines.append(f"| {k} | {m[k]} | {u.get(k, '')} |")
+    stalls = sorted(((int(float(v2)), k.replace("smsp__pcsamp_warps_issue_stalled_", "")) for k, v2 in m.items()
+                     if k.startswith("smsp__pcsamp_warps_issue_stalled_") and not k.endswith("not_issued")), reverse=True)
+    tot = sum(s for s, _ in stalls) or 1
+    lines += ["", "warp-state samples (pc sampling): " + ", ".join(f"{n} {100 * s / tot:.0f}%" for s, n in stalls[:7])]
+    # SASS mnemonic evidence
+    src = ncu_csv(rep, "source")
+    hi = next((i for i, r in enumerate(src) if "# Samples" in r), None)
+    if hi is not None:
+        hh = src[hi]; si = hh.index("Source")
+        ops = collections.Counter()
+        for r in src[hi + 1:]:
+            if len(r) > si and r[si]:
+                t = r[si].split()
+                op = t[1] if t[0].startswith("@") and len(t) > 1 else t[0]
+                ops[op.split(".")[0]] += 1
+        ev = {k: ops[k] for k in ("UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UBLKCP", "LDGSTS", "HMMA", "SYNCS", "UTCBAR") if ops.get(k)}
+        lines += ["", f"SASS instruction mix (static count): {dict(ops.most_common(12))}", "", f"Blackwell-native evidence: {ev}"]
+    if notes:
+        lines += ["", notes]
+    open(os.path.join(OUT, name + ".md"), "w").write("\n".join(lines) + "\n")
+    return m
+
+
+def launches(name):
+    p = os.path.join(ROOT, "gpurun_out", name + ".csv")
+    if not os.path.exists(p):
+        return
+    rows = [r for r in csv.reader(open(p)) if len(r) > 5]
+    h = rows[0]; ki, vi = h.index("Kernel Name"), h.index("Metric Value")
+    agg = collections.defaultdict(list)
+    for r in rows[1:]:
+        agg[r[ki].split("(")[0][-60:]].append(float(r[vi]))
+    tot = sum(sum(v) for v in agg.values())
+    lines = [f"# Launch list: one eager DiNNO round sequence (dist_mnist_PAPER, 10 nodes on 1 GPU)", "",
+             "ncu --metrics gpu__time_duration.sum (cold caches, serialised: compare SHARES)", "", "| kernel | launches | mean ns | share |", "|---|---|---|---|"]
+    for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+        lines.append(f"| {k} | {len(v)} | {sum(v) / len(v):.0f} | {100 * sum(v) / tot:.1f}% |")
+    open(os.path.join(OUT, name + ".md"), "w").write("\n".join(lines) + "\n")
+
+
+if __name__ == "__main__":
+    launches("launches_mnist")
+    summarize("mnist_train", "mnist_kernel<8,768,train> — fused MNIST conv-net forward+backward, 10 nodes x 8 slices", "")
+    summarize("mnist_eval", "mnist_kernel<8,768,eval> — forward-only validation pass", "")
+    summarize("dinno_update", "dinno_update_kernel<float> — fused neighbor pull + dual ascent + prox-gradient + Adam", "")
+    summarize("mlp_train", "mlp_train_kernel<256,2> — tcgen05/TMEM FourierNet forward+backward (7 nodes x 12500 rows)", "")
+    print(os.listdir(OUT))

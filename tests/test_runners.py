@@ -153,3 +153,34 @@ def test_scaling_runner(tmp_path, monkeypatch):
     dist_mnist_scaling.experiment(_write(str(tmp_path), "s.yaml", conf))
     out = glob.glob(os.path.join(str(tmp_path), "*_scaling_dinno_const_fied"))[0]
     assert {"0.gpickle", "1.gpickle", "0_results.pt", "1_results.pt"} <= set(os.listdir(out))
+
+
+def test_visualization_summary_and_tools(tmp_path, monkeypatch):
+    """Result inspection works on the files the runners write; waypoint tool builds valid paths."""
+    import nn_distributed_training_b200.data.mnist as M
+    from nn_distributed_training_b200.visualization import load_results, rounds_to_threshold, summarize_run
+    monkeypatch.setattr(dist_mnist_ex, "load_mnist",
+                        lambda d, train, **k: (M.synthetic_mnist(512 if train else 128, seed=int(train)), "synthetic"))
+    conf = _load("dist_mnist_template.yaml")
+    conf["experiment"].update(output_metadir=str(tmp_path), writeout=True)
+    conf["problem_configs"]["problem1"]["optimizer_config"]["outer_iterations"] = 5
+    conf["problem_configs"]["problem1"]["metrics_config"]["evaluate_frequency"] = 2
+    dist_mnist_ex.experiment(_write(str(tmp_path), "c.yaml", conf))
+    run = glob.glob(os.path.join(str(tmp_path), "*_dist_mnist_template"))[0]
+    s = summarize_run(run)
+    assert "dsgd" in s and 0.0 <= s["dsgd"]["final_top1_mean"] <= 1.0
+    r = rounds_to_threshold(load_results(run)["dsgd"], 0.0, 2)
+    assert r == 0
+    # waypoint authoring without a GUI
+    from nn_distributed_training_b200.floorplans.spline_paths import point_selector as ps
+    from nn_distributed_training_b200.floorplans.synthetic import make_floorplan
+    from PIL import Image
+    img, geo = make_floorplan(seed=0)
+    p = os.path.join(str(tmp_path), "floor.png")
+    Image.fromarray(img, mode="L").save(p)
+    c = geo["centers"][(0, 0)]
+    pts = ";".join(f"{c[0] + dx},{c[1] + dy}" for dx, dy in [(-30, -30), (30, -30), (30, 30), (-30, 30), (-30, -20)])
+    out = os.path.join(str(tmp_path), "wp.npy")
+    ps.main(["x", p, out, "--points", pts])
+    wp = np.load(out)
+    assert wp.shape == (5, 2) and np.abs(wp).max() <= 1.0
