@@ -46,6 +46,20 @@ struct MnistOp {
   void eval() { check(mnist::launch_eval(a, eval_ctas, cur_stream()), "mnist_eval"); }
 };
 
+struct GatherOp {
+  mnist::GatherArgs a{};
+  explicit GatherOp(const py::dict& d) {
+    a.x_host = ptr<const unsigned char>(d, "x_host"); a.y_host = ptr<const int64_t>(d, "y_host");
+    a.row_bytes = geti(d, "row_bytes"); a.x_stage = ptr<unsigned char>(d, "x_stage");
+    a.y_stage = ptr<int64_t>(d, "y_stage"); a.bs_stage = ptr<int>(d, "bs_stage");
+    a.P = geti(d, "P"); a.L = geti(d, "L"); a.batch = geti(d, "batch"); a.seed = geti(d, "seed"); a.node0 = geti(d, "node0");
+    a.shard_off = ptr<const int>(d, "shard_off"); a.shard_len = ptr<const int>(d, "shard_len");
+    a.calls0 = ptr<const int>(d, "calls0"); a.stage_round = ptr<int>(d, "stage_round");
+    a.done_ctr = ptr<unsigned int>(d, "done_ctr");
+  }
+  void launch() { check(mnist::launch_gather(a, cur_stream()), "gather_rows"); }
+};
+
 // -------------------------------------------------------------- consensus ----
 template <typename T>
 static consensus::Common<T> common_from(const py::dict& d) {
@@ -111,6 +125,7 @@ PYBIND11_MODULE(_C, m) {
       .def("update", &MnistOp::update)
       .def("train", &MnistOp::train)
       .def("eval", &MnistOp::eval);
+  py::class_<GatherOp>(m, "GatherOp").def(py::init<const py::dict&>()).def("launch", &GatherOp::launch);
   m.def("debug_batch_indices", [](int mm, int B, int call, int seed, int node, uint64_t out, uint64_t out_size) {
     check(mnist::launch_batch_indices(mm, B, call, seed, node, reinterpret_cast<int*>(out),
                                       reinterpret_cast<int*>(out_size), cur_stream()), "batch_indices");

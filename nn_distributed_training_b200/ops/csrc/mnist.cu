@@ -451,6 +451,50 @@ static cudaError_t launch_t(const Args& a, int S, bool train, int eval_ctas, cud
   return cudaGetLastError();
 }
 
+// ---- device-initiated H2D staging of one round's minibatches (one warp per row) -------------------------
+__global__ void __launch_bounds__(256) gather_rows_kernel(const GatherArgs a) {
+  // few, long-lived blocks: the staging copy must leave most SMs (and their register files) to the
+  // training kernels it overlaps with; each warp streams several rows with all loads of a row in flight
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rows = a.P * a.L * a.batch;
+  const int r = *a.stage_round;
+  const int n16 = a.row_bytes >> 4;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += nwarps) {
+    const int t = row % a.batch, l = (row / a.batch) % a.L, p = row / (a.batch * a.L);
+    const uint32_t m = (uint32_t)a.shard_len[l];
+    const BatchLoc loc = locate_batch((uint32_t)(a.calls0[l] + r * a.P + p), m, (uint32_t)a.batch);
+    if (t == 0 && lane == 0) a.bs_stage[p * a.L + l] = (int)loc.size;
+    if ((uint32_t)t < loc.size) {
+      const uint32_t key = mix_key((uint32_t)a.seed, (uint32_t)(a.node0 + l), loc.epoch);
+      const size_t src = (size_t)a.shard_off[l] + feistel_permute(loc.start + t, m, key);
+      const uint4* s4 = reinterpret_cast<const uint4*>(a.x_host + src * a.row_bytes);
+      uint4* d4 = reinterpret_cast<uint4*>(a.x_stage + (size_t)row * a.row_bytes);
+      uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
+      if (lane < n16) v0 = s4[lane];
+      if (lane + 32 < n16) v1 = s4[lane + 32];
+      if (lane < n16) d4[lane] = v0;
+      if (lane + 32 < n16) d4[lane + 32] = v1;
+      for (int i = lane + 64; i < n16; i += 32) d4[i] = s4[i];
+      if (lane == 0) a.y_stage[row] = a.y_host[src];
+    }
+  }
+  // last block advances the staged-round counter
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(a.done_ctr, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) { *a.done_ctr = 0; *a.stage_round = r + 1; }
+}
+cudaError_t launch_gather(const GatherArgs& a, cudaStream_t st) {
+  const int rows = a.P * a.L * a.batch;
+  int blocks = (rows * 32 + 255) / 256;
+  if (blocks > 24) blocks = 24;
+  gather_rows_kernel<<<blocks, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
 // debug/test helper: the sampler's row indices for one draw (mirrors data/sampler.py)
 __global__ void batch_indices_kernel(int m, int B, int call, int seed, int node, int* out, int* out_size) {
   const BatchLoc loc = locate_batch((uint32_t)call, (uint32_t)m, (uint32_t)B);

@@ -31,6 +31,23 @@ struct Args {
   unsigned char* val_correct;   // [L, n_val]
 };
 
+// Device-initiated host->device staging: the GPU pulls the next round's minibatch rows straight out of the
+// *pinned host* dataset (UVA pointer, PCIe reads) with the stateless sampler and writes them to a device
+// staging set.  No CPU work per round.
+struct GatherArgs {
+  const unsigned char* x_host;   // pinned host rows [M_total, row_bytes]
+  const int64_t* y_host;         // pinned host labels [M_total]
+  int row_bytes;
+  unsigned char* x_stage;        // device [P, L, B, row_bytes]
+  int64_t* y_stage;              // device [P, L, B]
+  int* bs_stage;                 // device [P, L]
+  int P, L, batch, seed, node0;
+  const int* shard_off; const int* shard_len;
+  const int* calls0;             // [L] draw counters at round 0 of the stream
+  int* stage_round;              // [1] device counter of staged rounds (advanced by this kernel)
+  unsigned int* done_ctr;        // [1]
+};
+cudaError_t launch_gather(const GatherArgs& a, cudaStream_t st);
 cudaError_t launch_train(const Args& a, int spb, int S, cudaStream_t st);
 cudaError_t launch_eval(const Args& a, int ctas_per_node, cudaStream_t st);
 cudaError_t launch_batch_indices(int m, int B, int call, int seed, int node, int* out, int* out_size, cudaStream_t st);

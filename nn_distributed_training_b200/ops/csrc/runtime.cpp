@@ -54,6 +54,9 @@ class HostBatchLoader {
   // slot holding the batches of the next round to consume (blocks until assembled)
   int acquire() {
     py::gil_scoped_release rel;
+    return acquire_nogil();
+  }
+  int acquire_nogil() {
     std::unique_lock<std::mutex> lk(mu_);
     const int64_t want = next_consume_;
     const int slot = (int)(want % nslots_);
@@ -134,7 +137,120 @@ static void cuda_check(cudaError_t e, const char* what) {
   if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
 }
 
+// Native per-round driver of the host-fed pipeline.  Round r uses device staging set (r & 1):
+//   copy stream   : wait(consumed[b]) -> H2D x/y/bs from the loader's pinned slot -> record(copied[b])
+//                   -> host callback releases the slot back to the loader threads
+//   compute stream: wait(copied[b]) -> launch the captured round graph of set b (kernels + D2H loss)
+//                   -> record(consumed[b])
+// so the H2D copy of round r+1 overlaps the kernels of round r and Python is out of the loop.
+class HostFedRunner {
+ public:
+  struct Copy { uint64_t dst, src_off; size_t bytes; };
+  HostFedRunner(HostBatchLoader* loader, std::vector<uint64_t> graph_execs, uint64_t compute_stream,
+                std::vector<uint64_t> slot_x, std::vector<uint64_t> slot_y, std::vector<uint64_t> slot_bs,
+                std::vector<uint64_t> stage_x, std::vector<uint64_t> stage_y, std::vector<uint64_t> stage_bs,
+                size_t x_bytes, size_t y_bytes, size_t bs_bytes)
+      : loader_(loader), execs_(std::move(graph_execs)), compute_(reinterpret_cast<cudaStream_t>(compute_stream)),
+        sx_(std::move(slot_x)), sy_(std::move(slot_y)), sb_(std::move(slot_bs)), dx_(std::move(stage_x)),
+        dy_(std::move(stage_y)), db_(std::move(stage_bs)), xb_(x_bytes), yb_(y_bytes), bb_(bs_bytes) {
+    cuda_check(cudaStreamCreateWithFlags(&copy_, cudaStreamNonBlocking), "cudaStreamCreate");
+    for (int b = 0; b < 2; ++b) {
+      cuda_check(cudaEventCreateWithFlags(&copied_[b], cudaEventDisableTiming), "cudaEventCreate");
+      cuda_check(cudaEventCreateWithFlags(&consumed_[b], cudaEventDisableTiming), "cudaEventCreate");
+    }
+  }
+  ~HostFedRunner() {
+    cudaStreamSynchronize(copy_);
+    for (int b = 0; b < 2; ++b) { cudaEventDestroy(copied_[b]); cudaEventDestroy(consumed_[b]); }
+    cudaStreamDestroy(copy_);
+  }
+
+  void run(int rounds) {
+    py::gil_scoped_release rel;
+    for (int i = 0; i < rounds; ++i, ++round_) {
+      const int b = (int)(round_ & 1);
+      const int slot = loader_->acquire_nogil();
+      if (round_ >= 2) cuda_check(cudaStreamWaitEvent(copy_, consumed_[b], 0), "wait consumed");
+      cuda_check(cudaMemcpyAsync(reinterpret_cast<void*>(dx_[b]), reinterpret_cast<void*>(sx_[slot]), xb_, cudaMemcpyHostToDevice, copy_), "h2d x");
+      cuda_check(cudaMemcpyAsync(reinterpret_cast<void*>(dy_[b]), reinterpret_cast<void*>(sy_[slot]), yb_, cudaMemcpyHostToDevice, copy_), "h2d y");
+      cuda_check(cudaMemcpyAsync(reinterpret_cast<void*>(db_[b]), reinterpret_cast<void*>(sb_[slot]), bb_, cudaMemcpyHostToDevice, copy_), "h2d bs");
+      cuda_check(cudaEventRecord(copied_[b], copy_), "record copied");
+      auto* rel_arg = new std::pair<HostBatchLoader*, int>(loader_, slot);
+      cuda_check(cudaLaunchHostFunc(copy_, &HostFedRunner::release_cb, rel_arg), "host func");
+      cuda_check(cudaStreamWaitEvent(compute_, copied_[b], 0), "wait copied");
+      cuda_check(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(execs_[b]), compute_), "graph launch");
+      cuda_check(cudaEventRecord(consumed_[b], compute_), "record consumed");
+    }
+  }
+  int64_t rounds_done() const { return round_; }
+
+ private:
+  static void CUDART_CB release_cb(void* p) {
+    auto* a = static_cast<std::pair<HostBatchLoader*, int>*>(p);
+    a->first->release(a->second);
+    delete a;
+  }
+  HostBatchLoader* loader_;
+  std::vector<uint64_t> execs_;
+  cudaStream_t compute_, copy_ = nullptr;
+  std::vector<uint64_t> sx_, sy_, sb_, dx_, dy_, db_;
+  size_t xb_, yb_, bb_;
+  cudaEvent_t copied_[2], consumed_[2];
+  int64_t round_ = 0;
+};
+
+// Two-stream round driver for device-initiated staging: copy graph (GPU pulls the next round's rows from pinned
+// host memory) on a side stream, round graph (kernels + D2H loss read) on the compute stream, double buffered.
+class PullRunner {
+ public:
+  PullRunner(std::vector<uint64_t> copy_execs, std::vector<uint64_t> round_execs, uint64_t compute_stream)
+      : copy_execs_(std::move(copy_execs)), round_execs_(std::move(round_execs)),
+        compute_(reinterpret_cast<cudaStream_t>(compute_stream)) {
+    cuda_check(cudaStreamCreateWithFlags(&copy_, cudaStreamNonBlocking), "cudaStreamCreate");
+    for (int b = 0; b < 2; ++b) {
+      cuda_check(cudaEventCreateWithFlags(&copied_[b], cudaEventDisableTiming), "cudaEventCreate");
+      cuda_check(cudaEventCreateWithFlags(&consumed_[b], cudaEventDisableTiming), "cudaEventCreate");
+    }
+  }
+  ~PullRunner() {
+    cudaStreamSynchronize(copy_);
+    for (int b = 0; b < 2; ++b) { cudaEventDestroy(copied_[b]); cudaEventDestroy(consumed_[b]); }
+    cudaStreamDestroy(copy_);
+  }
+  // stage round `round_` (and keep one round of look-ahead), then run it
+  void run(int rounds) {
+    py::gil_scoped_release rel;
+    for (int i = 0; i < rounds; ++i, ++round_) {
+      if (staged_ == round_) stage();          // first call: nothing staged yet
+      stage();                                 // look-ahead: round_ + 1 copies while round_ computes
+      const int b = (int)(round_ & 1);
+      cuda_check(cudaStreamWaitEvent(compute_, copied_[b], 0), "wait copied");
+      cuda_check(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(round_execs_[b]), compute_), "round graph");
+      cuda_check(cudaEventRecord(consumed_[b], compute_), "record consumed");
+    }
+  }
+  int64_t rounds_done() const { return round_; }
+
+ private:
+  void stage() {
+    if (staged_ > round_ + 1) return;
+    const int b = (int)(staged_ & 1);
+    if (staged_ >= 2) cuda_check(cudaStreamWaitEvent(copy_, consumed_[b], 0), "wait consumed");
+    cuda_check(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(copy_execs_[b]), copy_), "copy graph");
+    cuda_check(cudaEventRecord(copied_[b], copy_), "record copied");
+    ++staged_;
+  }
+  std::vector<uint64_t> copy_execs_, round_execs_;
+  cudaStream_t compute_, copy_ = nullptr;
+  cudaEvent_t copied_[2], consumed_[2];
+  int64_t round_ = 0, staged_ = 0;
+};
+
 void bind_runtime(py::module& m) {
+  py::class_<PullRunner>(m, "PullRunner")
+      .def(py::init<std::vector<uint64_t>, std::vector<uint64_t>, uint64_t>())
+      .def("run", &PullRunner::run)
+      .def("rounds_done", &PullRunner::rounds_done);
   py::class_<HostBatchLoader>(m, "HostBatchLoader")
       .def(py::init<uint64_t, uint64_t, int, std::vector<int>, std::vector<int>, std::vector<int64_t>, int, int, int,
                     int, std::vector<uint64_t>, std::vector<uint64_t>, std::vector<uint64_t>, int>())
@@ -142,6 +258,12 @@ void bind_runtime(py::module& m) {
       .def("release", &HostBatchLoader::release)
       .def("stop", &HostBatchLoader::stop)
       .def("rounds_assembled", &HostBatchLoader::rounds_assembled);
+  py::class_<HostFedRunner>(m, "HostFedRunner")
+      .def(py::init<HostBatchLoader*, std::vector<uint64_t>, uint64_t, std::vector<uint64_t>, std::vector<uint64_t>,
+                    std::vector<uint64_t>, std::vector<uint64_t>, std::vector<uint64_t>, std::vector<uint64_t>, size_t,
+                    size_t, size_t>(), py::keep_alive<1, 2>())
+      .def("run", &HostFedRunner::run)
+      .def("rounds_done", &HostFedRunner::rounds_done);
 
   // ---- CUDA IPC (legacy handles) for peer mapping of caching-allocator blocks ------------
   m.def("ipc_get_handle", [](uint64_t ptr) {

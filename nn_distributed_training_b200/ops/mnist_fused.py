@@ -74,12 +74,18 @@ class FusedMnist:
         self.calls.copy_(torch.as_tensor(self.pr.calls[pl.lo: pl.lo + pl.L].astype(np.int32)))
 
     # ---- host-fed batches (end-to-end input pipeline) -----------------------
-    def enable_host_feed(self, steps_per_round: int, nslots: int = 4, threads: int = 4):
-        """Switch to the host-fed input pipeline: the dataset stays in host memory, a
-        native multi-threaded loader (csrc/runtime.cpp) assembles every round's
-        minibatches into a ring of pinned slots, and each round performs one H2D copy
-        of its inputs and one D2H read of its losses.  This is the path ``bench.py``
-        times end to end; the default pipeline keeps shards resident in HBM."""
+    def enable_host_feed(self, steps_per_round: int, nslots: int = 4, threads: int = 4, mode: str = "gpu_pull"):
+        """Switch to the host-fed input pipeline: the dataset stays in (pinned) host memory and
+        every round's minibatches cross PCIe; each round also reads its losses back (D2H).
+        This is the path ``bench.py`` times end to end; the default keeps shards in HBM.
+
+        ``mode="gpu_pull"``: a staging kernel on a side stream pulls the *next* round's rows
+        straight out of the pinned host dataset (device-initiated H2D, in-kernel sampler) while
+        the current round computes — no CPU work per round.
+        ``mode="cpu_loader"``: native loader threads (csrc/runtime.cpp) assemble rounds into a
+        ring of pinned slots and the runner issues one ``cudaMemcpyAsync`` per round."""
+        if mode == "gpu_pull":
+            return self._enable_gpu_pull(steps_per_round)
         pr, dev = self.pr, self.pr.device
         P, L, B = int(steps_per_round), self.L, self.B
         xb = 1 if self.x_is_u8 else 4
@@ -89,16 +95,20 @@ class FusedMnist:
         self.x_pin = torch.empty(nslots, P, L, B, 784, dtype=self.x.dtype, **kw)
         self.y_pin = torch.empty(nslots, P, L, B, dtype=torch.int64, **kw)
         self.bs_pin = torch.empty(nslots, P, L, dtype=torch.int32, **kw)
-        self.x_stage = torch.zeros(P, L, B, 784, dtype=self.x.dtype, device=dev)
-        self.y_stage = torch.zeros(P, L, B, dtype=torch.int64, device=dev)
-        self.bs_stage = torch.zeros(P, L, dtype=torch.int32, device=dev)
+        # two device staging sets: the H2D copy of round r+1 overlaps the kernels of round r
+        self.x_stage = torch.zeros(2, P, L, B, 784, dtype=self.x.dtype, device=dev)
+        self.y_stage = torch.zeros(2, P, L, B, dtype=torch.int64, device=dev)
+        self.bs_stage = torch.zeros(2, P, L, dtype=torch.int32, device=dev)
         self.loss_host = torch.zeros(L, self.S, dtype=torch.float32, **kw)
         self.direct_ops = []
-        for p in range(P):
-            d = dict(self.base)
-            d.update(direct=1, x=self.x_stage[p].data_ptr(), y=self.y_stage[p].data_ptr(),
-                     direct_bs=self.bs_stage[p].data_ptr())
-            self.direct_ops.append(self.ext.MnistOp(d))
+        for b in range(2):
+            ops = []
+            for p in range(P):
+                d = dict(self.base)
+                d.update(direct=1, x=self.x_stage[b, p].data_ptr(), y=self.y_stage[b, p].data_ptr(),
+                         direct_bs=self.bs_stage[b, p].data_ptr())
+                ops.append(self.ext.MnistOp(d))
+            self.direct_ops.append(ops)
         pl = pr.placement
         calls0 = [int(c) for c in pr.calls[pl.lo: pl.lo + pl.L]]
         self.loader = self.ext.HostBatchLoader(
@@ -108,16 +118,73 @@ class FusedMnist:
             [self.x_pin[s].data_ptr() for s in range(nslots)],
             [self.y_pin[s].data_ptr() for s in range(nslots)],
             [self.bs_pin[s].data_ptr() for s in range(nslots)], threads)
-        self.host_feed = dict(P=P, nslots=nslots,
+        self.host_feed = dict(P=P, nslots=nslots, mode="cpu_loader",
                               h2d_bytes=P * L * B * (784 * xb + 8) + P * L * 4,
                               d2h_bytes=L * self.S * 4)
         return self.host_feed
 
-    def stage_copy(self, slot: int):
-        """Enqueue this round's H2D input copy (pinned ring slot -> device staging)."""
-        self.x_stage.copy_(self.x_pin[slot], non_blocking=True)
-        self.y_stage.copy_(self.y_pin[slot], non_blocking=True)
-        self.bs_stage.copy_(self.bs_pin[slot], non_blocking=True)
+    def _enable_gpu_pull(self, steps_per_round: int):
+        pr, dev = self.pr, self.pr.device
+        P, L, B = int(steps_per_round), self.L, self.B
+        xb = 1 if self.x_is_u8 else 4
+        self.host_x = self.x.cpu().contiguous().pin_memory()
+        self.host_y = self.y.cpu().contiguous().pin_memory()
+        self.x_stage = torch.zeros(2, P, L, B, 784, dtype=self.x.dtype, device=dev)
+        self.y_stage = torch.zeros(2, P, L, B, dtype=torch.int64, device=dev)
+        self.bs_stage = torch.zeros(2, P, L, dtype=torch.int32, device=dev)
+        self.loss_host = torch.zeros(L, self.S, dtype=torch.float32, pin_memory=True)
+        pl = pr.placement
+        self.calls0 = torch.as_tensor(pr.calls[pl.lo: pl.lo + pl.L].astype(np.int32), device=dev)
+        self.stage_round = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.stage_done = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.direct_ops, self.gather_ops = [], []
+        for b in range(2):
+            ops = []
+            for p in range(P):
+                d = dict(self.base)
+                d.update(direct=1, x=self.x_stage[b, p].data_ptr(), y=self.y_stage[b, p].data_ptr(),
+                         direct_bs=self.bs_stage[b, p].data_ptr())
+                ops.append(self.ext.MnistOp(d))
+            self.direct_ops.append(ops)
+            self.gather_ops.append(self.ext.GatherOp(dict(
+                x_host=self.host_x.data_ptr(), y_host=self.host_y.data_ptr(), row_bytes=784 * xb,
+                x_stage=self.x_stage[b].data_ptr(), y_stage=self.y_stage[b].data_ptr(),
+                bs_stage=self.bs_stage[b].data_ptr(), P=P, L=L, batch=B, seed=pr.seed, node0=pl.lo,
+                shard_off=self.shard_off.data_ptr(), shard_len=self.shard_len.data_ptr(),
+                calls0=self.calls0.data_ptr(), stage_round=self.stage_round.data_ptr(),
+                done_ctr=self.stage_done.data_ptr())))
+        self.loader = None
+        self.host_feed = dict(P=P, nslots=2, mode="gpu_pull",
+                              h2d_bytes=P * L * B * (784 * xb + 8), d2h_bytes=L * self.S * 4)
+        return self.host_feed
+
+    def make_pull_runner(self, round_graphs):
+        """Capture the two staging graphs and build the native two-stream driver."""
+        copy_graphs = []
+        side = torch.cuda.Stream(device=self.pr.device)
+        for b in range(2):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                self.gather_ops[b].launch()
+            copy_graphs.append(g)
+        self._graphs = (copy_graphs, round_graphs)
+        stream = torch.cuda.current_stream(self.pr.device).cuda_stream
+        self.runner = self.ext.PullRunner([g.raw_cuda_graph_exec() for g in copy_graphs],
+                                          [g.raw_cuda_graph_exec() for g in round_graphs], stream)
+        return self.runner
+
+    def make_runner(self, graphs, nslots):
+        """Native per-round driver (csrc/runtime.cpp: HostFedRunner) over the two captured round graphs."""
+        self._graphs = graphs
+        stream = torch.cuda.current_stream(self.pr.device).cuda_stream
+        self.runner = self.ext.HostFedRunner(
+            self.loader, [g.raw_cuda_graph_exec() for g in graphs], stream,
+            [self.x_pin[s].data_ptr() for s in range(nslots)], [self.y_pin[s].data_ptr() for s in range(nslots)],
+            [self.bs_pin[s].data_ptr() for s in range(nslots)],
+            [self.x_stage[b].data_ptr() for b in range(2)], [self.y_stage[b].data_ptr() for b in range(2)],
+            [self.bs_stage[b].data_ptr() for b in range(2)],
+            self.x_pin[0].numel() * self.x_pin.element_size(), self.y_pin[0].numel() * 8, self.bs_pin[0].numel() * 4)
+        return self.runner
 
     def loss_readback(self):
         """Enqueue the D2H read of the round's per-node losses."""

@@ -66,18 +66,18 @@ class RoundProgram:
                 if init_draws:
                     raise NotImplementedError("host-fed pipeline with DSGT init_grads")
                 pr.fused.enable_host_feed(self.dpr, nslots=int(pr.conf.get("host_slots", 4)),
-                                          threads=int(pr.conf.get("host_threads", 4)))
+                                          threads=int(pr.conf.get("host_threads", 4)),
+                                          mode=pr.conf.get("host_gather", "gpu_pull"))
                 self.host_mode = True
-                self._slot_graphs: Dict[int, torch.cuda.CUDAGraph] = {}
-                self._slot_events = {}
-                self._inflight = []
+                self._runner = None
+                self._stage_set = 0
 
     def grads(self, p: int = 0):
         pr = self.pr
         if pr.fused is None:
             pr.compute_grads()
         elif self.host_mode:
-            pr.fused.direct_ops[p].train()
+            pr.fused.direct_ops[self._stage_set][p].train()
         else:
             pr.fused.launch()
 
@@ -93,28 +93,26 @@ class RoundProgram:
             self.pr.count_draws_all(1)
 
     def _run_host_fed(self, rounds: int):
-        """One graph replay per round: H2D copy of the round's inputs from the pinned
-        ring slot, the round's kernels, D2H read of the losses."""
+        """Host-fed rounds: the native runner issues, per round, the H2D copy of that round's
+        inputs (copy stream), the captured round graph (kernels + D2H loss read) and the slot
+        hand-back to the loader threads — Python only counts."""
         fz = self.pr.fused
-        for _ in range(rounds):
-            while len(self._inflight) >= fz.host_feed["nslots"] - 1:
-                s_old, ev = self._inflight.pop(0)
-                ev.synchronize()          # its H2D copy is done: the loader may refill the slot
-                fz.loader.release(s_old)
-            slot = fz.loader.acquire()
-            g = self._slot_graphs.get(slot)
-            if g is None:
+        if self._runner is None:
+            graphs = []
+            for b in range(2):
+                self._stage_set = b
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    fz.stage_copy(slot)
                     _round_ops(self.opt, self.eng, self.grads)
                     fz.loss_readback()
-                self._slot_graphs[slot] = g
-            g.replay()
-            ev = torch.cuda.Event()
-            ev.record()
-            self._inflight.append((slot, ev))
-            self._count(1)
+                graphs.append(g)
+            if fz.host_feed["mode"] == "gpu_pull":
+                self._runner = fz.make_pull_runner(graphs)
+            else:
+                self._runner = fz.make_runner(graphs, fz.host_feed["nslots"])
+        # graphs were captured on torch's capture stream but are launched on the current stream
+        self._runner.run(rounds)
+        self._count(rounds)
 
     def run(self, rounds: int):
         """Execute ``rounds`` consecutive rounds starting at the device round counter."""

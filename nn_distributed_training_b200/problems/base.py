@@ -136,8 +136,8 @@ class ConsensusProblem:
         """Advance the draw counters of *every* node (all nodes draw in lockstep;
         each rank mirrors the whole network so epoch/forward-count metrics and the
         dynamic-graph schedule need no communication)."""
-        for g in range(self.N):
-            self._count_draw(g, times)
+        self.calls += times
+        self.forward_cnt += times * self.train_batch_size
 
     def plan_graphs(self, oits: int, k0: int, draws_per_round: int, init_draws: int = 0, refresh: bool = True):
         """Communication graph of every round ``0..oits-1`` (static here).  Problems
