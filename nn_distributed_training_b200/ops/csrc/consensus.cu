@@ -105,6 +105,73 @@ NNDT_DEVINL T* pub_row(const Common<T>& c, int par, int chan, int l) {
   return c.pub + ((size_t)(par * c.C + chan) * c.pub_L + l) * c.n_pad;
 }
 
+// ---- complete-graph mode -----------------------------------------------------------------------
+// network-wide sum of channel `chan` at element i for parity `par`
+NNDT_DEVINL Pack<float> ld_reduce_mc(const float* p) {
+  Pack<float> r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3])
+               : "l"(p)
+               : "memory");
+  return r;
+}
+NNDT_DEVINL Pack<double> ld_reduce_mc(const double* p) {
+  Pack<double> r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f64 %0, [%1];" : "=d"(r.v[0]) : "l"(p) : "memory");
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f64 %0, [%1];" : "=d"(r.v[1]) : "l"(p + 1) : "memory");
+  return r;
+}
+template <typename T>
+NNDT_DEVINL Pack<T> network_sum(const Common<T>& c, int par, int chan, int i) {
+  const size_t off = (size_t)(par * c.C + chan) * c.n_pad + i;
+  if (c.sum_mc != nullptr) return ld_reduce_mc(c.sum_mc + off);
+  return ldv(c.sum_local + off);
+}
+// every rank's partial sum of round k must be in place before the in-switch reduction reads it
+template <typename T>
+NNDT_DEVINL void wait_all_sums(const Common<T>& c, int k) {
+  if (c.world > 1) {
+    if ((int)threadIdx.x < c.world && (int)threadIdx.x != c.rank) {
+      const long long t0 = clock64();
+      while (ld_acquire_sys(c.sum_flags + threadIdx.x) < k + 1) {
+        if (clock64() - t0 > kSpinLimit) { *c.err = 1; break; }
+      }
+    }
+    __syncthreads();
+  }
+}
+// S_local[par][chan] = sum over this rank's nodes of the published rows of round k
+template <typename T>
+__global__ void __launch_bounds__(THREADS) local_sum_kernel(const Common<T> c) {
+  constexpr int N = Vec<T>::N;
+  const RoundInfo<T> ri = round_info(c);
+  for (int ch = 0; ch < c.C; ++ch) {
+    for (int i = (blockIdx.x * THREADS + threadIdx.x) * N; i < c.n_pad; i += gridDim.x * THREADS * N) {
+      Pack<T> s = ldv(pub_row(c, ri.par, ch, 0) + i);
+      for (int l = 1; l < c.L; ++l) {
+        const Pack<T> q = ldv(pub_row(c, ri.par, ch, l) + i);
+#pragma unroll
+        for (int u = 0; u < N; ++u) s.v[u] += q.v[u];
+      }
+      stv(c.sum_local + (size_t)(ri.par * c.C + ch) * c.n_pad + i, s);
+    }
+  }
+  // last block: tell every peer that this rank's partial sum of round k is ready
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(c.done_ctr, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (is_last) {
+    if (threadIdx.x == 0) *c.done_ctr = 0;
+    if (c.world > 1) {
+      __threadfence_system();
+      if ((int)threadIdx.x < c.world && (int)threadIdx.x != c.rank)
+        st_release_sys(reinterpret_cast<int*>(c.peer_sum_flag[threadIdx.x]), ri.k + 1);
+    }
+  }
+}
+
 template <typename T>
 NNDT_DEVINL Pack<T> sum_partials(const Common<T>& c, int l, int i) {
   const T* gp = c.grad_part + (size_t)l * c.S * c.n_pad + i;
@@ -127,7 +194,7 @@ __global__ void __launch_bounds__(THREADS) dinno_update_kernel(const DinnoArgs<T
   const int deg = c.deg[ri.gid * c.L + l];
   const T rho = c.rho[ri.k], lr = c.lr[ri.k];
   const bool first = a.step == 0, last = a.step == a.pits - 1;
-  if (first) wait_neighbors(c, ri.gid, l, ri.k);
+  if (first) { if (c.sum_mode) wait_all_sums(c, ri.k); else wait_neighbors(c, ri.gid, l, ri.k); }
 
   const T b1 = (T)0.9, b2 = (T)0.999, eps = (T)1e-8, wd = (T)1e-2;
   const int t = a.persistent ? ri.k * a.pits + a.step + 1 : a.step + 1;
@@ -145,10 +212,16 @@ __global__ void __launch_bounds__(THREADS) dinno_update_kernel(const DinnoArgs<T
       thk = th;  // live row == theta^k at round start
 #pragma unroll
       for (int u = 0; u < N; ++u) dl.v[u] = (T)0;
-      for (int e = 0; e < deg; ++e) {
-        const Pack<T> q = ldv(nbr_row(c, ri.gid, l, e, ri.par, 0) + i);
+      if (c.sum_mode) {   // delta = S_all - N theta_i   (every other node is a neighbor)
+        const Pack<T> sall = network_sum(c, ri.par, 0, i);
 #pragma unroll
-        for (int u = 0; u < N; ++u) dl.v[u] += q.v[u] - thk.v[u];
+        for (int u = 0; u < N; ++u) dl.v[u] = sall.v[u] - (T)c.n_total * thk.v[u];
+      } else {
+        for (int e = 0; e < deg; ++e) {
+          const Pack<T> q = ldv(nbr_row(c, ri.gid, l, e, ri.par, 0) + i);
+#pragma unroll
+          for (int u = 0; u < N; ++u) dl.v[u] += q.v[u] - thk.v[u];
+        }
       }
       du = ldv(a.dual + row + i);
 #pragma unroll
@@ -201,11 +274,18 @@ __global__ void __launch_bounds__(THREADS) dsgd_mix_kernel(const Common<T> c) {
   const int l = blockIdx.y;
   const RoundInfo<T> ri = round_info(c);
   const int deg = c.deg[ri.gid * c.L + l];
-  wait_neighbors(c, ri.gid, l, ri.k);
+  if (c.sum_mode) wait_all_sums(c, ri.k); else wait_neighbors(c, ri.gid, l, ri.k);
   const T ws = c.self_w[ri.gid * c.L + l];
   const T* w = c.nbr_w + (size_t)(ri.gid * c.L + l) * c.dmax;
   const size_t row = (size_t)l * c.n_pad;
   for (int i = (blockIdx.x * THREADS + threadIdx.x) * N; i < c.n_pad; i += gridDim.x * THREADS * N) {
+    if (c.sum_mode) {     // W = 11^T / N: the mixed row is the network mean
+      Pack<T> th = network_sum(c, ri.par, 0, i);
+#pragma unroll
+      for (int u = 0; u < N; ++u) th.v[u] *= (T)1 / (T)c.n_total;
+      stv(c.theta + row + i, th);
+      continue;
+    }
     Pack<T> th = ldv(c.theta + row + i);
 #pragma unroll
     for (int u = 0; u < N; ++u) th.v[u] *= ws;
@@ -261,13 +341,21 @@ __global__ void __launch_bounds__(THREADS) dsgt_mix_kernel(const DsgtArgs<T> a) 
   const int l = blockIdx.y;
   const RoundInfo<T> ri = round_info(c);
   const int deg = c.deg[ri.gid * c.L + l];
-  wait_neighbors(c, ri.gid, l, ri.k);
+  if (c.sum_mode) wait_all_sums(c, ri.k); else wait_neighbors(c, ri.gid, l, ri.k);
   const T alpha = c.alpha[ri.k];
   const T ws = c.self_w[ri.gid * c.L + l];
   const T* w = c.nbr_w + (size_t)(ri.gid * c.L + l) * c.dmax;
   const size_t row = (size_t)l * c.n_pad;
   const T* ys = pub_row(c, ri.par, 1, l);
   for (int i = (blockIdx.x * THREADS + threadIdx.x) * N; i < c.n_pad; i += gridDim.x * THREADS * N) {
+    if (c.sum_mode) {
+      const Pack<T> st = network_sum(c, ri.par, 0, i), sy = network_sum(c, ri.par, 1, i);
+      Pack<T> th;
+#pragma unroll
+      for (int u = 0; u < N; ++u) th.v[u] = (st.v[u] - alpha * sy.v[u]) / (T)c.n_total;
+      stv(c.theta + row + i, th);
+      continue;
+    }
     Pack<T> th = ldv(c.theta + row + i);
     const Pack<T> y = ldv(ys + i);
 #pragma unroll
@@ -295,14 +383,21 @@ __global__ void __launch_bounds__(THREADS) dsgt_track_kernel(const DsgtArgs<T> a
   const size_t row = (size_t)l * c.n_pad;
   const T* ys = pub_row(c, ri.par, 1, l);
   for (int i = (blockIdx.x * THREADS + threadIdx.x) * N; i < c.n_pad; i += gridDim.x * THREADS * N) {
-    Pack<T> y = ldv(ys + i);
+    Pack<T> y;
+    if (c.sum_mode) {
+      y = network_sum(c, ri.par, 1, i);
 #pragma unroll
-    for (int u = 0; u < N; ++u) y.v[u] *= ws;
-    for (int e = 0; e < deg; ++e) {
-      const Pack<T> qy = ldv(nbr_row(c, ri.gid, l, e, ri.par, 1) + i);
-      const T we = w[e];
+      for (int u = 0; u < N; ++u) y.v[u] *= (T)1 / (T)c.n_total;
+    } else {
+      y = ldv(ys + i);
 #pragma unroll
-      for (int u = 0; u < N; ++u) y.v[u] += we * qy.v[u];
+      for (int u = 0; u < N; ++u) y.v[u] *= ws;
+      for (int e = 0; e < deg; ++e) {
+        const Pack<T> qy = ldv(nbr_row(c, ri.gid, l, e, ri.par, 1) + i);
+        const T we = w[e];
+#pragma unroll
+        for (int u = 0; u < N; ++u) y.v[u] += we * qy.v[u];
+      }
     }
     const Pack<T> gn = sum_partials(c, l, i);
     const Pack<T> go = ldv(a.g_old + row + i);
@@ -324,6 +419,11 @@ static dim3 grid_for(const Common<T>& c) {
   return dim3(gx, c.L);
 }
 
+template <typename T> cudaError_t launch_local_sum(const Common<T>& c, cudaStream_t st) {
+  const int per_block = THREADS * Vec<T>::N;
+  local_sum_kernel<T><<<(c.n_pad + per_block - 1) / per_block, THREADS, 0, st>>>(c);
+  return cudaGetLastError();
+}
 template <typename T> cudaError_t launch_dinno_update(const DinnoArgs<T>& a, cudaStream_t st) {
   dinno_update_kernel<T><<<grid_for(a.c), THREADS, 0, st>>>(a);
   return cudaGetLastError();
@@ -350,6 +450,7 @@ template <typename T> cudaError_t launch_dsgt_track(const DsgtArgs<T>& a, cudaSt
 }
 
 #define NNDT_INST(T)                                                                  \
+  template cudaError_t launch_local_sum<T>(const Common<T>&, cudaStream_t);           \
   template cudaError_t launch_dinno_update<T>(const DinnoArgs<T>&, cudaStream_t);     \
   template cudaError_t launch_dsgd_mix<T>(const Common<T>&, cudaStream_t);            \
   template cudaError_t launch_dsgd_step<T>(const Common<T>&, cudaStream_t);           \

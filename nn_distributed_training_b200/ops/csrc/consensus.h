@@ -43,6 +43,16 @@ struct Common {
   int world, rank;
   unsigned int* done_ctr;     // [1] last-block detection
   int* err;                   // [1] set on spin timeout
+  // complete-graph ("sum") mode: Metropolis weights are uniform 1/N, so every aggregate is a function of
+  // S = sum over ALL nodes.  Each rank reduces its local rows into `sum_local` and the consumers fetch the
+  // network-wide sum either with one NVLS in-switch reduction (multimem.ld_reduce over `sum_mc`) or, on a
+  // single GPU, straight from `sum_local`.
+  int sum_mode;               // 0 = pointer-table neighbors, 1 = complete graph via sums
+  int n_total;                // N (all nodes of the graph)
+  T* sum_local;               // [2 parity, C, n_pad] this rank's partial sums (symmetric memory)
+  const T* sum_mc;            // multicast mapping of sum_local (nullptr: single GPU)
+  int* sum_flags;             // [world] "partial sum of round k ready" flags written by peers
+  const int64_t* peer_sum_flag;  // [world]
 };
 
 template <typename T>
@@ -64,6 +74,7 @@ template <typename T> cudaError_t launch_dsgd_step(const Common<T>& c, cudaStrea
 template <typename T> cudaError_t launch_dsgt_init(const DsgtArgs<T>& a, cudaStream_t st);
 template <typename T> cudaError_t launch_dsgt_mix(const DsgtArgs<T>& a, cudaStream_t st);
 template <typename T> cudaError_t launch_dsgt_track(const DsgtArgs<T>& a, cudaStream_t st);
+template <typename T> cudaError_t launch_local_sum(const Common<T>& c, cudaStream_t st);
 
 }  // namespace consensus
 }  // namespace nndt

@@ -105,6 +105,28 @@ class ConsensusEngine:
             torch.cuda.synchronize(dev)
             ctx.barrier()
 
+        # ---- complete graph: uniform Metropolis weights -> aggregates are functions of the network sum ----
+        self.sum_mode = (G == 1 and topos[0].is_complete() and pr.N > 1
+                         and opt.conf.get("complete_graph_mode", "sum") == "sum")
+        self.sum_buf = self.sum_flag_buf = None
+        sum_mc = None
+        if self.sum_mode:
+            self.sum_buf = SymmetricBuffer((2, self.C, n_pad), self.dtype, ctx)
+            self.sum_flag_buf = SymmetricBuffer((max(ctx.world_size, 1),), torch.int32, ctx)
+            self.sum_flag_buf.local.fill_(k0)
+            if ctx.is_distributed:
+                if self.sum_buf.multicast_ptr:
+                    sum_mc = self.sum_buf.multicast_ptr      # NVLS: one in-switch reduction per element
+                else:
+                    self.sum_mode = False                    # no multicast mapping on this fabric: pointer table
+                torch.cuda.synchronize(dev)
+                ctx.barrier()
+        peer_sum_flag = np.zeros(max(ctx.world_size, 1), dtype=np.int64)
+        if self.sum_mode:
+            for r in range(ctx.world_size):
+                peer_sum_flag[r] = self.sum_flag_buf.peer_ptrs[r] + 4 * ctx.rank
+        self.t_peer_sum_flag = torch.as_tensor(peer_sum_flag, device=dev)
+
         # ---- gradient source --------------------------------------------------------
         if pr.fused is not None:
             grad_part, S, calls = pr.fused.grad_part, pr.fused.S, pr.fused.calls
@@ -124,6 +146,9 @@ class ConsensusEngine:
         # published buffer is allocated with the max count, so pass that as the row count of pub
         d["L"] = L
         d["pub_L"] = self.Lpub
+        if self.sum_mode:
+            d.update(sum_mode=1, n_total=pr.N, sum_local=self.sum_buf.local.data_ptr(), sum_mc=sum_mc,
+                     sum_flags=self.sum_flag_buf.local.data_ptr(), peer_sum_flag=self.t_peer_sum_flag.data_ptr())
         if opt.alg_name == "dinno":
             d.update(dual=opt.duals.data_ptr(), delta=opt.delta.data_ptr(),
                      m=None if opt.m is None else opt.m.data_ptr(),

@@ -25,6 +25,8 @@ MAX_ROUNDS_PER_GRAPH = 64
 
 def _round_ops(opt, eng, grads):
     alg = opt.alg_name
+    if eng.sum_mode:
+        eng.op.local_sum()   # complete graph: per-rank partial sums feeding the NVLS reduction
     if alg == "dinno":
         for p in range(opt.pits):
             grads(p)

@@ -68,7 +68,9 @@ def main():
             rel = ((theta - ref).norm() / ref.norm()).item()
             vd = (vl - pr1.metrics["validation_loss"][-1]).abs().max().item()
             good = bad < 5e-3 and rel < 1e-2 and vd < 1e-3
-            print(f"[dist] {alg} world={ctx.world_size} graph={args.graph} bad={bad:.2e} rel={rel:.2e} "
+            eng = getattr(getattr(opt, "_program", None), "eng", None)
+            how = "" if eng is None else f" sum_mode={eng.sum_mode} mc={bool(eng.sum_buf and eng.sum_buf.multicast_ptr)}"
+            print(f"[dist] {alg} world={ctx.world_size} graph={args.graph}{how} bad={bad:.2e} rel={rel:.2e} "
                   f"val_diff={vd:.2e} {'OK' if good else 'MISMATCH'}", flush=True)
             ok = ok and good
         ctx.barrier()

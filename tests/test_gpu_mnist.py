@@ -112,12 +112,12 @@ DSGT_C = {"alg_name": "dsgt", "alpha": 0.02, "init_grads": True, "outer_iteratio
 @pytest.mark.parametrize("cls,conf", [(DiNNO, DINNO), (DiNNO, dict(DINNO, primal_optimizer="sgd")),
                                       (DiNNO, dict(DINNO, primal_optimizer="adamw", persistant_primal_opt=True)),
                                       (DSGD, DSGD_C), (DSGT, DSGT_C), (DSGT, dict(DSGT_C, init_grads=False))])
-@pytest.mark.parametrize("graph", ["cycle", "wheel"])
+@pytest.mark.parametrize("graph", ["cycle", "wheel", "complete"])
 def test_fused_training_matches_torch_ops(cls, conf, graph):
     """Whole fused round programs (CUDA graph replay) vs the PyTorch consensus ops driving
     the same fused forward/backward, 7 rounds, fp32."""
     N = 5
-    G = nx.cycle_graph(N) if graph == "cycle" else nx.wheel_graph(N)
+    G = {"cycle": nx.cycle_graph(N), "wheel": nx.wheel_graph(N), "complete": nx.complete_graph(N)}[graph]
     a = _problem(N, 32, "fused", conf, graph=G, eval_every=3)
     b = _problem(N, 32, "fused", conf, graph=G, eval_every=3)
     b.arena.theta.copy_(a.arena.theta)
@@ -125,6 +125,7 @@ def test_fused_training_matches_torch_ops(cls, conf, graph):
     ob = cls(b, DEV, dict(copy.deepcopy(conf), consensus_backend="torch"))
     oa.train()
     ob.train()
+    assert oa._program.eng.sum_mode == (graph == "complete")     # complete graph -> network-sum kernels
     _assert_mostly_close(a.arena.theta, b.arena.theta)
     assert a.forward_cnt == b.forward_cnt
     assert len(a.metrics["validation_loss"]) == len(b.metrics["validation_loss"]) == 3
