@@ -74,6 +74,7 @@ class ConsensusProblem:
         self.N = len(train_sets) if graph is None else graph.number_of_nodes()
         self.placement = Placement(self.N, self.ctx.world_size, self.ctx.rank)
         self.graph = graph
+        self._init_faults()
 
         # ---- parameters: one arena row per local node --------------------
         p0 = next(base_model.parameters())
@@ -143,7 +144,9 @@ class ConsensusProblem:
         """Communication graph of every round ``0..oits-1`` (static here).  Problems
         with a data-driven graph override this; it is what lets a dynamic topology
         live in device tables indexed by the round counter."""
-        return [self.graph] * oits
+        if self._faults is None:
+            return [self.graph] * oits
+        return [self.faulted_graph(self._base_graph, k) if refresh else self._base_graph for k in range(oits)]
 
     def _batch(self, g: int):
         l = self.placement.local_index(g)
@@ -190,8 +193,34 @@ class ConsensusProblem:
     # graph
     # ------------------------------------------------------------------
     def update_graph(self):
-        """Static graph: nothing to do (dist_mnist_problem.py:100-102)."""
+        """Static graph: nothing to do (dist_mnist_problem.py:100-102) — unless link-drop fault
+        injection is configured, in which case round ``r`` uses the faulted graph."""
+        if self._faults is not None:
+            self.graph = self.faulted_graph(self._base_graph, self._graph_round)
+            self._graph_round += 1
         return
+
+    # ---- fault injection (SURVEY §5.3: the reference has none) ---------------------------
+    def _init_faults(self):
+        """``fault_injection: {link_drop_prob: p, seed: s, from_round: a, to_round: b}`` in the
+        problem config drops every edge independently with probability ``p`` in rounds
+        ``[a, b)`` — the same mechanism as a time-varying graph, so it runs on the fused path
+        through the planned topology tables.  Nodes left without neighbors take local steps."""
+        f = self.conf.get("fault_injection")
+        self._faults = dict(f) if f else None
+        self._graph_round = 0
+        self._base_graph = self.graph
+
+    def faulted_graph(self, graph, rnd: int):
+        f = self._faults
+        if f is None or graph is None or not (f.get("from_round", 0) <= rnd < f.get("to_round", 10 ** 12)):
+            return graph
+        rng = np.random.default_rng([int(f.get("seed", 0)), int(rnd)])
+        g = graph.copy()
+        edges = sorted(tuple(sorted(e)) for e in graph.edges() if e[0] != e[1])
+        drop = rng.random(len(edges)) < float(f["link_drop_prob"])
+        g.remove_edges_from([e for e, d in zip(edges, drop) if d])
+        return g
 
     def topology(self) -> Topology:
         return self._topo_cache.get(self.graph)

@@ -61,6 +61,9 @@ class DistOnlineDensityProblem(DensityProblemBase):
     # ---- graph ----------------------------------------------------------------------
     def update_graph(self):
         self.graph, connected = graph_generation.euclidean_disk_graph(self.positions(), self.comm_radius)
+        if self._faults is not None:
+            self.graph = self.faulted_graph(self.graph, self._graph_round)
+            self._graph_round += 1
         if not connected and self.ctx.is_main:
             print("** WARNING: the communication graph is not connected. **")
         return
@@ -73,6 +76,7 @@ class DistOnlineDensityProblem(DensityProblemBase):
             if refresh or frozen is None:
                 calls = base + init_draws + max(0, k - k0) * draws_per_round
                 g, _ = graph_generation.euclidean_disk_graph(self.positions(calls), self.comm_radius)
+                g = self.faulted_graph(g, k)
                 frozen = g
             out.append(frozen if not refresh else g)
         return out

@@ -206,3 +206,19 @@ def test_checkpoint_resume_is_bit_exact(tmp_path, alg):
     o2.train()
     assert torch.equal(second.arena.theta, full.arena.theta)
     assert second.forward_cnt == full.forward_cnt
+
+
+def test_link_drop_fault_injection_changes_graph_and_training_survives():
+    conf = {"alg_name": "dinno", "rho_init": 0.5, "rho_scaling": 1.0, "outer_iterations": 5, "primal_iterations": 1,
+            "primal_optimizer": "sgd", "persistant_primal_opt": False, "primal_lr_start": 0.01,
+            "primal_lr_finish": 0.01, "lr_decay_type": "constant", "profile": False}
+    pr = _mnist_problem(5, nx.cycle_graph(5), conf)
+    pr.conf["fault_injection"] = {"link_drop_prob": 0.5, "seed": 3, "from_round": 1, "to_round": 4}
+    pr._init_faults()
+    plan = pr.plan_graphs(5, 0, 1)
+    assert plan[0].number_of_edges() == 5 and plan[4].number_of_edges() == 5
+    assert any(g.number_of_edges() < 5 for g in plan[1:4])
+    DiNNO(pr, "cpu", conf).train()
+    assert torch.isfinite(pr.arena.theta).all()
+    # the eager path walked the same graph sequence as the plan
+    assert pr._graph_round == 5
