@@ -107,25 +107,24 @@ NNDT_DEVINL T* pub_row(const Common<T>& c, int par, int chan, int l) {
 
 // ---- complete-graph mode -----------------------------------------------------------------------
 // network-wide sum of channel `chan` at element i for parity `par`
-NNDT_DEVINL Pack<float> ld_reduce_mc(const float* p) {
-  Pack<float> r;
-  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
-               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3])
-               : "l"(p)
-               : "memory");
-  return r;
-}
-NNDT_DEVINL Pack<double> ld_reduce_mc(const double* p) {
-  Pack<double> r;
-  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f64 %0, [%1];" : "=d"(r.v[0]) : "l"(p) : "memory");
-  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f64 %0, [%1];" : "=d"(r.v[1]) : "l"(p + 1) : "memory");
-  return r;
-}
+template <int N> struct DPack { double v[N]; };
 template <typename T>
-NNDT_DEVINL Pack<T> network_sum(const Common<T>& c, int par, int chan, int i) {
+NNDT_DEVINL DPack<Vec<T>::N> network_sum(const Common<T>& c, int par, int chan, int i) {
+  constexpr int N = Vec<T>::N;
   const size_t off = (size_t)(par * c.C + chan) * c.n_pad + i;
-  if (c.sum_mc != nullptr) return ld_reduce_mc(c.sum_mc + off);
-  return ldv(c.sum_local + off);
+  DPack<N> r;
+  if (c.sum_mc != nullptr) {
+#pragma unroll
+    for (int u = 0; u < N; ++u)
+      asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f64 %0, [%1];" : "=d"(r.v[u]) : "l"(c.sum_mc + off + u) : "memory");
+  } else {
+#pragma unroll
+    for (int u = 0; u < N; u += 2) {
+      const double2 q = *reinterpret_cast<const double2*>(c.sum_local + off + u);
+      r.v[u] = q.x; r.v[u + 1] = q.y;
+    }
+  }
+  return r;
 }
 // every rank's partial sum of round k must be in place before the in-switch reduction reads it
 template <typename T>
@@ -147,13 +146,17 @@ __global__ void __launch_bounds__(THREADS) local_sum_kernel(const Common<T> c) {
   const RoundInfo<T> ri = round_info(c);
   for (int ch = 0; ch < c.C; ++ch) {
     for (int i = (blockIdx.x * THREADS + threadIdx.x) * N; i < c.n_pad; i += gridDim.x * THREADS * N) {
-      Pack<T> s = ldv(pub_row(c, ri.par, ch, 0) + i);
-      for (int l = 1; l < c.L; ++l) {
+      double s[N];
+#pragma unroll
+      for (int u = 0; u < N; ++u) s[u] = 0.0;
+      for (int l = 0; l < c.L; ++l) {
         const Pack<T> q = ldv(pub_row(c, ri.par, ch, l) + i);
 #pragma unroll
-        for (int u = 0; u < N; ++u) s.v[u] += q.v[u];
+        for (int u = 0; u < N; ++u) s[u] += (double)q.v[u];
       }
-      stv(c.sum_local + (size_t)(ri.par * c.C + ch) * c.n_pad + i, s);
+      double* dst = c.sum_local + (size_t)(ri.par * c.C + ch) * c.n_pad + i;
+#pragma unroll
+      for (int u = 0; u < N; u += 2) *reinterpret_cast<double2*>(dst + u) = make_double2(s[u], s[u + 1]);
     }
   }
   // last block: tell every peer that this rank's partial sum of round k is ready
@@ -213,9 +216,9 @@ __global__ void __launch_bounds__(THREADS) dinno_update_kernel(const DinnoArgs<T
 #pragma unroll
       for (int u = 0; u < N; ++u) dl.v[u] = (T)0;
       if (c.sum_mode) {   // delta = S_all - N theta_i   (every other node is a neighbor)
-        const Pack<T> sall = network_sum(c, ri.par, 0, i);
+        const DPack<N> sall = network_sum(c, ri.par, 0, i);
 #pragma unroll
-        for (int u = 0; u < N; ++u) dl.v[u] = sall.v[u] - (T)c.n_total * thk.v[u];
+        for (int u = 0; u < N; ++u) dl.v[u] = (T)(sall.v[u] - (double)c.n_total * (double)thk.v[u]);
       } else {
         for (int e = 0; e < deg; ++e) {
           const Pack<T> q = ldv(nbr_row(c, ri.gid, l, e, ri.par, 0) + i);
@@ -280,9 +283,10 @@ __global__ void __launch_bounds__(THREADS) dsgd_mix_kernel(const Common<T> c) {
   const size_t row = (size_t)l * c.n_pad;
   for (int i = (blockIdx.x * THREADS + threadIdx.x) * N; i < c.n_pad; i += gridDim.x * THREADS * N) {
     if (c.sum_mode) {     // W = 11^T / N: the mixed row is the network mean
-      Pack<T> th = network_sum(c, ri.par, 0, i);
+      const DPack<N> sall = network_sum(c, ri.par, 0, i);
+      Pack<T> th;
 #pragma unroll
-      for (int u = 0; u < N; ++u) th.v[u] *= (T)1 / (T)c.n_total;
+      for (int u = 0; u < N; ++u) th.v[u] = (T)(sall.v[u] / (double)c.n_total);
       stv(c.theta + row + i, th);
       continue;
     }
@@ -349,10 +353,10 @@ __global__ void __launch_bounds__(THREADS) dsgt_mix_kernel(const DsgtArgs<T> a) 
   const T* ys = pub_row(c, ri.par, 1, l);
   for (int i = (blockIdx.x * THREADS + threadIdx.x) * N; i < c.n_pad; i += gridDim.x * THREADS * N) {
     if (c.sum_mode) {
-      const Pack<T> st = network_sum(c, ri.par, 0, i), sy = network_sum(c, ri.par, 1, i);
+      const DPack<N> st = network_sum(c, ri.par, 0, i), sy = network_sum(c, ri.par, 1, i);
       Pack<T> th;
 #pragma unroll
-      for (int u = 0; u < N; ++u) th.v[u] = (st.v[u] - alpha * sy.v[u]) / (T)c.n_total;
+      for (int u = 0; u < N; ++u) th.v[u] = (T)((st.v[u] - (double)alpha * sy.v[u]) / (double)c.n_total);
       stv(c.theta + row + i, th);
       continue;
     }
@@ -385,9 +389,9 @@ __global__ void __launch_bounds__(THREADS) dsgt_track_kernel(const DsgtArgs<T> a
   for (int i = (blockIdx.x * THREADS + threadIdx.x) * N; i < c.n_pad; i += gridDim.x * THREADS * N) {
     Pack<T> y;
     if (c.sum_mode) {
-      y = network_sum(c, ri.par, 1, i);
+      const DPack<N> sy = network_sum(c, ri.par, 1, i);
 #pragma unroll
-      for (int u = 0; u < N; ++u) y.v[u] *= (T)1 / (T)c.n_total;
+      for (int u = 0; u < N; ++u) y.v[u] = (T)(sy.v[u] / (double)c.n_total);
     } else {
       y = ldv(ys + i);
 #pragma unroll

@@ -49,8 +49,8 @@ struct Common {
   // single GPU, straight from `sum_local`.
   int sum_mode;               // 0 = pointer-table neighbors, 1 = complete graph via sums
   int n_total;                // N (all nodes of the graph)
-  T* sum_local;               // [2 parity, C, n_pad] this rank's partial sums (symmetric memory)
-  const T* sum_mc;            // multicast mapping of sum_local (nullptr: single GPU)
+  double* sum_local;          // [2 parity, C, n_pad] this rank's partial sums, always fp64: S - N theta_i cancels
+  const double* sum_mc;       //   catastrophically in fp32 near consensus.  sum_mc = multicast mapping (or nullptr)
   int* sum_flags;             // [world] "partial sum of round k ready" flags written by peers
   const int64_t* peer_sum_flag;  // [world]
 };

@@ -111,7 +111,7 @@ class ConsensusEngine:
         self.sum_buf = self.sum_flag_buf = None
         sum_mc = None
         if self.sum_mode:
-            self.sum_buf = SymmetricBuffer((2, self.C, n_pad), self.dtype, ctx)
+            self.sum_buf = SymmetricBuffer((2, self.C, n_pad), torch.float64, ctx)   # fp64: S - N*theta cancels in fp32
             self.sum_flag_buf = SymmetricBuffer((max(ctx.world_size, 1),), torch.int32, ctx)
             self.sum_flag_buf.local.fill_(k0)
             if ctx.is_distributed:
