@@ -23,7 +23,17 @@ from .engine import ConsensusEngine
 MAX_ROUNDS_PER_GRAPH = 64
 
 
+def _nvtx(name):
+    """NVTX range per phase (visible in Nsight / torch.profiler traces; no-op cost when not profiling)."""
+    return torch.cuda.nvtx.range(name)
+
+
 def _round_ops(opt, eng, grads):
+    with _nvtx(f"consensus_round/{opt.alg_name}"):
+        _round_ops_impl(opt, eng, grads)
+
+
+def _round_ops_impl(opt, eng, grads):
     alg = opt.alg_name
     if eng.sum_mode:
         eng.op.local_sum()   # complete graph: per-rank partial sums feeding the NVLS reduction

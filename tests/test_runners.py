@@ -184,3 +184,14 @@ def test_visualization_summary_and_tools(tmp_path, monkeypatch):
     ps.main(["x", p, out, "--points", pts])
     wp = np.load(out)
     assert wp.shape == (5, 2) and np.abs(wp).max() <= 1.0
+
+
+def test_centralized_baseline(monkeypatch):
+    import nn_distributed_training_b200.data.mnist as M
+    from nn_distributed_training_b200.experiments import centralized
+    from nn_distributed_training_b200.models import MNISTConvNet
+    tr, va = M.synthetic_mnist(600, seed=0), M.synthetic_mnist(200, seed=1)
+    torch.manual_seed(0)
+    hist = centralized.train_centralized(MNISTConvNet(3, 5, 64), torch.nn.NLLLoss(), tr, va, "cpu", epochs=2, lr=0.005,
+                                         batch=50, verbose=False)
+    assert hist[-1]["top1_accuracy"] > 0.5 and hist[-1]["validation_loss"] < hist[0]["validation_loss"] * 1.5
