@@ -135,6 +135,13 @@ PYBIND11_MODULE(_C, m) {
     check(mnist::launch_batch_indices(mm, B, call, seed, node, reinterpret_cast<int*>(out),
                                       reinterpret_cast<int*>(out_size), cur_stream()), "batch_indices");
   });
+  m.def("consensus_metric", [](bool f64, uint64_t rows, int N, int n_pad, int local0, int L, uint64_t inv_norm,
+                               uint64_t out_pair, uint64_t out_mean) {
+    auto r = reinterpret_cast<const int64_t*>(rows);
+    auto a = reinterpret_cast<double*>(inv_norm); auto b = reinterpret_cast<double*>(out_pair); auto c = reinterpret_cast<double*>(out_mean);
+    check(f64 ? consensus::launch_consensus_metric<double>(r, N, n_pad, local0, L, a, b, c, cur_stream())
+              : consensus::launch_consensus_metric<float>(r, N, n_pad, local0, L, a, b, c, cur_stream()), "consensus_metric");
+  });
   bind_consensus<float>(m, "ConsensusOpF32");
   bind_consensus<double>(m, "ConsensusOpF64");
   bind_mlp(m);

@@ -415,6 +415,61 @@ __global__ void __launch_bounds__(THREADS) dsgt_track_kernel(const DsgtArgs<T> a
   finish_round(c, ri.k);
 }
 
+// ------------------------------------------------------------ consensus metric ----
+NNDT_DEVINL double block_sum(double v) {
+  __shared__ double red[THREADS / 32];
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < THREADS / 32; ++w) t += red[w];
+  return t;
+}
+template <typename T>
+__global__ void __launch_bounds__(THREADS) inv_norm_kernel(const int64_t* rows, int n_pad, double* inv_norm) {
+  const T* r = reinterpret_cast<const T*>(rows[blockIdx.x]);
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n_pad; i += THREADS) { const double v = (double)r[i]; acc += v * v; }
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) inv_norm[blockIdx.x] = 1.0 / fmax(sqrt(acc), 1e-12);   // F.normalize eps
+}
+// block (j, l): j < N -> pair distance to node j;  j == N -> distance to the mean of the normalised rows
+template <typename T>
+__global__ void __launch_bounds__(THREADS) consensus_metric_kernel(const int64_t* rows, int N, int n_pad, int local0,
+                                                                   const double* inv_norm, double* out_pair, double* out_mean) {
+  const int j = blockIdx.x, l = blockIdx.y, gi = local0 + l;
+  const T* ri = reinterpret_cast<const T*>(rows[gi]);
+  const double ni = inv_norm[gi];
+  double acc = 0.0;
+  if (j < N) {
+    const T* rj = reinterpret_cast<const T*>(rows[j]);
+    const double nj = inv_norm[j];
+    for (int e = threadIdx.x; e < n_pad; e += THREADS) {
+      const double d = (double)ri[e] * ni - (double)rj[e] * nj;
+      acc += d * d;
+    }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) out_pair[(size_t)l * N + j] = sqrt(acc);
+  } else {
+    for (int e = threadIdx.x; e < n_pad; e += THREADS) {
+      double mu = 0.0;
+      for (int q = 0; q < N; ++q) mu += (double)reinterpret_cast<const T*>(rows[q])[e] * inv_norm[q];
+      const double d = (double)ri[e] * ni - mu / (double)N;
+      acc += d * d;
+    }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) out_mean[l] = sqrt(acc);
+  }
+}
+template <typename T>
+cudaError_t launch_consensus_metric(const int64_t* rows, int N, int n_pad, int local0, int L, double* inv_norm,
+                                    double* out_pair, double* out_mean, cudaStream_t st) {
+  inv_norm_kernel<T><<<N, THREADS, 0, st>>>(rows, n_pad, inv_norm);
+  consensus_metric_kernel<T><<<dim3(N + 1, L), THREADS, 0, st>>>(rows, N, n_pad, local0, inv_norm, out_pair, out_mean);
+  return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------- launchers ----
 template <typename T>
 static dim3 grid_for(const Common<T>& c) {
@@ -455,6 +510,7 @@ template <typename T> cudaError_t launch_dsgt_track(const DsgtArgs<T>& a, cudaSt
 
 #define NNDT_INST(T)                                                                  \
   template cudaError_t launch_local_sum<T>(const Common<T>&, cudaStream_t);           \
+  template cudaError_t launch_consensus_metric<T>(const int64_t*, int, int, int, int, double*, double*, double*, cudaStream_t); \
   template cudaError_t launch_dinno_update<T>(const DinnoArgs<T>&, cudaStream_t);     \
   template cudaError_t launch_dsgd_mix<T>(const Common<T>&, cudaStream_t);            \
   template cudaError_t launch_dsgd_step<T>(const Common<T>&, cudaStream_t);           \

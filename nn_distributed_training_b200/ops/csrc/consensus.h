@@ -76,5 +76,12 @@ template <typename T> cudaError_t launch_dsgt_mix(const DsgtArgs<T>& a, cudaStre
 template <typename T> cudaError_t launch_dsgt_track(const DsgtArgs<T>& a, cudaStream_t st);
 template <typename T> cudaError_t launch_local_sum(const Common<T>& c, cudaStream_t st);
 
+// K6 consensus metric (problems/dist_mnist_problem.py:155-169): distances between L2-normalised parameter rows.
+// rows[j] is the device address of node j's current row (local, or a peer GPU's published row over NVLink).
+// out_pair [L, N] = |th_i/|th_i| - th_j/|th_j||,  out_mean [L] = |th_i/|th_i| - mean_j th_j/|th_j||   (fp64 accumulation)
+template <typename T>
+cudaError_t launch_consensus_metric(const int64_t* rows, int N, int n_pad, int local0, int L, double* inv_norm,
+                                    double* out_pair, double* out_mean, cudaStream_t st);
+
 }  // namespace consensus
 }  // namespace nndt

@@ -160,6 +160,33 @@ class ConsensusEngine:
         self.op = cls(d)
         self._keep = d
 
+    def consensus_metric(self, k: int):
+        """Fused consensus-error metric (csrc/consensus.cu: consensus_metric_kernel) on the rows published
+        for round ``k``: every rank pulls all N rows (local or NVLink peer) and produces the distance rows of
+        its own nodes; returns (pairwise [N, N], to-mean [N, 1]) gathered over ranks, as float64 CPU tensors."""
+        pr, pl, ctx, dev = self.pr, self.pr.placement, self.pr.ctx, self.pr.device
+        N, L, n_pad = pr.N, pl.L, self.pr.arena.n_pad
+        par = k & 1
+        itemsize = self.pub.element_size()
+        rows = np.zeros(N, dtype=np.int64)
+        for g in range(N):
+            r, lj = int(pl.node_rank[g]), int(pl.node_local[g])
+            rows[g] = self.pub_buf.peer_ptrs[r] + ((par * self.C) * self.Lpub + lj) * n_pad * itemsize
+        t_rows = torch.as_tensor(rows, device=dev)
+        inv = torch.empty(N, dtype=torch.float64, device=dev)
+        pair = torch.empty(L, N, dtype=torch.float64, device=dev)
+        mean = torch.empty(L, dtype=torch.float64, device=dev)
+        if ctx.is_distributed:
+            torch.cuda.synchronize(dev)
+            ctx.barrier()              # every rank's rows of round k are published and quiescent
+        self.ext.consensus_metric(self.dtype == torch.float64, t_rows.data_ptr(), N, n_pad, pl.lo, L,
+                                  inv.data_ptr(), pair.data_ptr(), mean.data_ptr())
+        d_all = pr.gather_rows(pair).cpu()
+        d_mean = pr.gather_rows(mean.reshape(-1, 1)).cpu()
+        if ctx.is_distributed:
+            ctx.barrier()              # nobody starts overwriting published rows while a peer still reads
+        return d_all, d_mean
+
     def check(self):
         if int(self.err.item()) != 0:
             raise RuntimeError("consensus kernel timed out waiting for a peer's published round")

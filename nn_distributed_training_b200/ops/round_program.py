@@ -69,6 +69,8 @@ class RoundProgram:
                                 refresh=getattr(opt, "refresh_graph", True))
         self.eng = ConsensusEngine(opt, graphs)
         self.graph_plan = graphs
+        # evaluation between rounds can use the fused consensus-metric kernel on the published rows
+        pr._metric_engine = (self.eng, lambda: opt.k)
         self.capturable = pr.fused is not None and os.environ.get("NNDT_NO_GRAPH", "0") != "1"
         self._graphs: Dict[int, torch.cuda.CUDAGraph] = {}
         self.host_mode = False

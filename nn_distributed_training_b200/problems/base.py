@@ -239,6 +239,10 @@ class ConsensusProblem:
     # metrics
     # ------------------------------------------------------------------
     def _consensus_metric(self):
+        eng = getattr(self, "_metric_engine", None)
+        if eng is not None:     # fused path: P2P pull of every node's published row, fp64 accumulation
+            d_all, d_mean = eng[0].consensus_metric(eng[1]())
+            return d_all.to(torch.get_default_dtype()), d_mean.to(torch.get_default_dtype())
         with torch.no_grad():
             d_all, d_mean = consensus_ref.consensus_error(self.all_theta())
         return d_all, d_mean
