@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <utility>
 
 #define NNDT_DEVINL __device__ __forceinline__
 
@@ -45,6 +46,25 @@ NNDT_DEVINL float4 ld_stream_f4(const float* p) {
                : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
                : "l"(p));
   return r;
+}
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------
+// Kernels of a round are launched with cudaLaunchAttributeProgrammaticStreamSerialization: a kernel may
+// start while its predecessor drains.  Convention in this repo: every kernel executes pdl_wait() before it
+// touches anything the *immediately preceding* kernel wrote, and only then pdl_launch_dependents() — so when
+// a kernel's pre-wait prologue runs, everything two or more kernels back is complete and visible.
+NNDT_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+NNDT_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 // cp.async helpers (LDGSTS)

@@ -142,6 +142,8 @@ NNDT_DEVINL void wait_all_sums(const Common<T>& c, int k) {
 // S_local[par][chan] = sum over this rank's nodes of the published rows of round k
 template <typename T>
 __global__ void __launch_bounds__(THREADS) local_sum_kernel(const Common<T> c) {
+  pdl_wait();
+  pdl_launch_dependents();
   constexpr int N = Vec<T>::N;
   const RoundInfo<T> ri = round_info(c);
   for (int ch = 0; ch < c.C; ++ch) {
@@ -208,6 +210,10 @@ __global__ void __launch_bounds__(THREADS) dinno_update_kernel(const DinnoArgs<T
 
   const size_t row = (size_t)l * c.n_pad;
   const T* thk_row = pub_row(c, ri.par, 0, l);
+  // The grid covers the row exactly once (one vector per thread), so all state that the preceding
+  // forward/backward kernel does not write is fetched BEFORE the programmatic-dependency wait and
+  // overlaps that kernel's tail; only the gradient partials are read after it.
+  bool waited = false;
   for (int i = (blockIdx.x * THREADS + threadIdx.x) * N; i < c.n_pad; i += gridDim.x * THREADS * N) {
     Pack<T> th = ldv(c.theta + row + i);
     Pack<T> thk, dl, du;
@@ -236,6 +242,17 @@ __global__ void __launch_bounds__(THREADS) dinno_update_kernel(const DinnoArgs<T
       dl = ldv(a.delta + row + i);
       du = ldv(a.dual + row + i);
     }
+    Pack<T> m, v;
+    if (a.opt != kSGD) {
+      if (fresh) {
+#pragma unroll
+        for (int u = 0; u < N; ++u) { m.v[u] = (T)0; v.v[u] = (T)0; }
+      } else {
+        m = ldv(a.m + row + i);
+        v = ldv(a.v + row + i);
+      }
+    }
+    if (!waited) { pdl_wait(); pdl_launch_dependents(); waited = true; }
     const Pack<T> gl = sum_partials(c, l, i);
     Pack<T> g;
 #pragma unroll
@@ -245,14 +262,6 @@ __global__ void __launch_bounds__(THREADS) dinno_update_kernel(const DinnoArgs<T
 #pragma unroll
       for (int u = 0; u < N; ++u) th.v[u] -= lr * g.v[u];
     } else {
-      Pack<T> m, v;
-      if (fresh) {
-#pragma unroll
-        for (int u = 0; u < N; ++u) { m.v[u] = (T)0; v.v[u] = (T)0; }
-      } else {
-        m = ldv(a.m + row + i);
-        v = ldv(a.v + row + i);
-      }
 #pragma unroll
       for (int u = 0; u < N; ++u) {
         if (a.opt == kAdamW) th.v[u] *= ((T)1 - lr * wd);
@@ -266,6 +275,7 @@ __global__ void __launch_bounds__(THREADS) dinno_update_kernel(const DinnoArgs<T
     stv(c.theta + row + i, th);
     if (last) stv(pub_row(c, ri.par ^ 1, 0, l) + i, th);
   }
+  if (!waited) { pdl_wait(); pdl_launch_dependents(); }
   if (c.calls != nullptr && blockIdx.x == 0 && threadIdx.x == 0) c.calls[l] += 1;
   if (last) finish_round(c, ri.k);
 }
@@ -273,6 +283,8 @@ __global__ void __launch_bounds__(THREADS) dinno_update_kernel(const DinnoArgs<T
 // ------------------------------------------------------------------- DSGD ----
 template <typename T>
 __global__ void __launch_bounds__(THREADS) dsgd_mix_kernel(const Common<T> c) {
+  pdl_wait();
+  pdl_launch_dependents();
   constexpr int N = Vec<T>::N;
   const int l = blockIdx.y;
   const RoundInfo<T> ri = round_info(c);
@@ -305,6 +317,8 @@ __global__ void __launch_bounds__(THREADS) dsgd_mix_kernel(const Common<T> c) {
 
 template <typename T>
 __global__ void __launch_bounds__(THREADS) dsgd_step_kernel(const Common<T> c) {
+  pdl_wait();
+  pdl_launch_dependents();
   constexpr int N = Vec<T>::N;
   const int l = blockIdx.y;
   const RoundInfo<T> ri = round_info(c);
@@ -326,6 +340,8 @@ __global__ void __launch_bounds__(THREADS) dsgd_step_kernel(const Common<T> c) {
 // channel 0 of the published buffer is theta, channel 1 the gradient tracker y.
 template <typename T>
 __global__ void __launch_bounds__(THREADS) dsgt_init_kernel(const DsgtArgs<T> a) {
+  pdl_wait();
+  pdl_launch_dependents();
   const Common<T>& c = a.c;
   constexpr int N = Vec<T>::N;
   const int l = blockIdx.y;
@@ -340,6 +356,8 @@ __global__ void __launch_bounds__(THREADS) dsgt_init_kernel(const DsgtArgs<T> a)
 
 template <typename T>
 __global__ void __launch_bounds__(THREADS) dsgt_mix_kernel(const DsgtArgs<T> a) {
+  pdl_wait();
+  pdl_launch_dependents();
   const Common<T>& c = a.c;
   constexpr int N = Vec<T>::N;
   const int l = blockIdx.y;
@@ -377,6 +395,8 @@ __global__ void __launch_bounds__(THREADS) dsgt_mix_kernel(const DsgtArgs<T> a) 
 
 template <typename T>
 __global__ void __launch_bounds__(THREADS) dsgt_track_kernel(const DsgtArgs<T> a) {
+  pdl_wait();
+  pdl_launch_dependents();
   const Common<T>& c = a.c;
   constexpr int N = Vec<T>::N;
   const int l = blockIdx.y;
@@ -480,32 +500,25 @@ static dim3 grid_for(const Common<T>& c) {
 
 template <typename T> cudaError_t launch_local_sum(const Common<T>& c, cudaStream_t st) {
   const int per_block = THREADS * Vec<T>::N;
-  local_sum_kernel<T><<<(c.n_pad + per_block - 1) / per_block, THREADS, 0, st>>>(c);
-  return cudaGetLastError();
+  return launch_pdl(local_sum_kernel<T>, dim3((c.n_pad + per_block - 1) / per_block), dim3(THREADS), 0, st, c);
 }
 template <typename T> cudaError_t launch_dinno_update(const DinnoArgs<T>& a, cudaStream_t st) {
-  dinno_update_kernel<T><<<grid_for(a.c), THREADS, 0, st>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(dinno_update_kernel<T>, grid_for(a.c), dim3(THREADS), 0, st, a);
 }
 template <typename T> cudaError_t launch_dsgd_mix(const Common<T>& c, cudaStream_t st) {
-  dsgd_mix_kernel<T><<<grid_for(c), THREADS, 0, st>>>(c);
-  return cudaGetLastError();
+  return launch_pdl(dsgd_mix_kernel<T>, grid_for(c), dim3(THREADS), 0, st, c);
 }
 template <typename T> cudaError_t launch_dsgd_step(const Common<T>& c, cudaStream_t st) {
-  dsgd_step_kernel<T><<<grid_for(c), THREADS, 0, st>>>(c);
-  return cudaGetLastError();
+  return launch_pdl(dsgd_step_kernel<T>, grid_for(c), dim3(THREADS), 0, st, c);
 }
 template <typename T> cudaError_t launch_dsgt_init(const DsgtArgs<T>& a, cudaStream_t st) {
-  dsgt_init_kernel<T><<<grid_for(a.c), THREADS, 0, st>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(dsgt_init_kernel<T>, grid_for(a.c), dim3(THREADS), 0, st, a);
 }
 template <typename T> cudaError_t launch_dsgt_mix(const DsgtArgs<T>& a, cudaStream_t st) {
-  dsgt_mix_kernel<T><<<grid_for(a.c), THREADS, 0, st>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(dsgt_mix_kernel<T>, grid_for(a.c), dim3(THREADS), 0, st, a);
 }
 template <typename T> cudaError_t launch_dsgt_track(const DsgtArgs<T>& a, cudaStream_t st) {
-  dsgt_track_kernel<T><<<grid_for(a.c), THREADS, 0, st>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(dsgt_track_kernel<T>, grid_for(a.c), dim3(THREADS), 0, st, a);
 }
 
 #define NNDT_INST(T)                                                                  \

@@ -184,6 +184,9 @@ __global__ void __launch_bounds__(NT, 1) mnist_kernel(const Args a) {
   const int tid = threadIdx.x;
   const int l = blockIdx.y;
   const float* th = a.theta + (size_t)l * a.n_pad;
+  // everything below reads parameters / draw counters written by the preceding consensus kernel
+  pdl_wait();
+  pdl_launch_dependents();
 
   // ---- stage fc1 weights (async) and the small tensors ----------------------------------
   {
@@ -444,7 +447,7 @@ static cudaError_t launch_t(const Args& a, int S, bool train, int eval_ctas, cud
   cudaError_t e = train ? prepare_once<SPB, true>() : prepare_once<SPB, false>();
   if (e != cudaSuccess) return e;
   if (train) {
-    mnist_kernel<SPB, kNT, true><<<dim3(S, a.L), kNT, smem, st>>>(a);
+    return launch_pdl(mnist_kernel<SPB, kNT, true>, dim3(S, a.L), dim3(kNT), smem, st, a);
   } else {
     mnist_kernel<SPB, kNT, false><<<dim3(eval_ctas, a.L), kNT, smem, st>>>(a);
   }
