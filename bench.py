@@ -147,7 +147,7 @@ class StepTimer:
 
 
 # -------------------------------------------------------------------- ours ----
-def build_problem(ctx, n_nodes, oc, eval_every, extra=None, samples_per_node=SAMPLES_PER_NODE):
+def build_problem(ctx, n_nodes, oc, eval_every, extra=None, samples_per_node=SAMPLES_PER_NODE, backend="fused"):
     import networkx as nx
     import torch
     from nn_distributed_training_b200.data.mnist import synthetic_mnist
@@ -167,7 +167,7 @@ def build_problem(ctx, n_nodes, oc, eval_every, extra=None, samples_per_node=SAM
     torch.manual_seed(0)
     base = MNISTConvNet(3, 5, 64)
     return DistMNISTProblem(nx.cycle_graph(n_nodes), base, torch.nn.NLLLoss(), train, val, ctx.device,
-                            prob_conf(oc, eval_every, extra), ctx=ctx, backend="fused")
+                            prob_conf(oc, eval_every, extra), ctx=ctx, backend=backend)
 
 
 class _Stub:
@@ -279,6 +279,37 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------- NCCL baseline ----
+def run_nccl_baseline(args):
+    """'The NCCL baseline' of SURVEY §0(ii): the same update rules as plain PyTorch — autograd/cuDNN
+    forward+backward per node, NCCL all_gather of the parameter rows, torch ops for mixing and Adam —
+    one rank per GPU, fp32.  This is the path a solution that 'only calls NCCL' would be."""
+    import torch
+    import torch.distributed as dist
+    from nn_distributed_training_b200.optimizers import DiNNO
+    from nn_distributed_training_b200.parallel.context import DistContext
+
+    ctx = DistContext.from_env(use_cuda=True)
+    n_nodes = NODES_PER_GPU * args.gpus
+    W, K = args.warmup, args.steps
+    oc = dict(opt_conf(max(PAPER_ROUNDS, W + K + 1)), consensus_backend="torch")
+    pr = build_problem(ctx, n_nodes, oc, 10 ** 9, extra={"backend": "torch"}, samples_per_node=REF_SAMPLES_PER_NODE, backend="torch")
+    opt = DiNNO(pr, ctx.device, oc)
+    opt.run_rounds(W)
+    torch.cuda.synchronize(); ctx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); opt.run_rounds(K); e1.record(); torch.cuda.synchronize(); ctx.barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=ctx.device)
+    ms = float(ctx.all_reduce_max(t).item())
+    if ctx.is_main:
+        print(json.dumps({"metric": "consensus node-rounds/sec (DiNNO, dist_mnist_PAPER; rounds/sec x graph nodes)",
+                          "impl": "nccl_baseline (PyTorch eager + NCCL all_gather, this repo's torch path)", "value": n_nodes * K / (ms / 1e3),
+                          "unit": "node-rounds/s", "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": ms / K,
+                          "dtype": "fp32", "data": "synthetic", "higher_is_better": True, "scaling": "weak"}))
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
 # --------------------------------------------------------------- reference ----
 def ensure_reference():
     ref = os.path.join(ROOT, "baseline", "_ref")
@@ -373,12 +404,16 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl"])
     args = ap.parse_args()
     if args.impl == "reference":
         if "--steps" not in " ".join(sys.argv):
             args.steps = 100
         run_reference(args)
+    elif args.impl == "nccl":
+        if "--steps" not in " ".join(sys.argv):
+            args.steps = 100
+        run_nccl_baseline(args)
     else:
         run_ours(args)
 
