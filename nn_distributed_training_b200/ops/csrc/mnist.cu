@@ -60,6 +60,7 @@ struct Smem {
   int label[SPB];
   float valid[SPB];
   unsigned char arg[SPB * FC1_IN];
+  alignas(8) uint64_t w1_bar;           // TMA transaction barrier of the fc1 weight staging
 };
 
 template <int SPB, int NT>
@@ -188,14 +189,15 @@ __global__ void __launch_bounds__(NT, 1) mnist_kernel(const Args a) {
   pdl_wait();
   pdl_launch_dependents();
 
-  // ---- stage fc1 weights (async) and the small tensors ----------------------------------
+  // ---- stage fc1 weights with the TMA engine (one bulk copy per 1728-byte row into the padded smem rows,
+  //      completion tracked by an mbarrier transaction count) and the small tensors with plain loads -------
   {
     const float* w1g = th + a.off_w1;
-    for (int o = tid; o < HID * (FC1_IN / 4); o += NT) {
-      const int j = o / (FC1_IN / 4), k4 = o - j * (FC1_IN / 4);
-      cp_async16(sm.w1 + j * W1_STRIDE + 4 * k4, w1g + j * FC1_IN + 4 * k4);
+    if (tid == 0) {
+      mbarrier_init(&sm.w1_bar, 1);
+      mbarrier_expect_tx(&sm.w1_bar, HID * FC1_IN * 4);
+      for (int j = 0; j < HID; ++j) tma_bulk_g2s(sm.w1 + j * W1_STRIDE, w1g + j * FC1_IN, FC1_IN * 4, &sm.w1_bar);
     }
-    cp_async_commit();
     if (tid < 75) sm.wc[tid] = th[a.off_wc + tid];
     if (tid < 3) sm.wc[75 + tid] = th[a.off_bc + tid];
     if (tid < HID) sm.b1[tid] = th[a.off_b1 + tid];
@@ -242,7 +244,7 @@ __global__ void __launch_bounds__(NT, 1) mnist_kernel(const Args a) {
     load_images<SPB, NT>(sm, a, tid);
     __syncthreads();
     conv_relu_pool<SPB, NT>(sm, tid);
-    cp_async_wait<0>();
+    mbarrier_wait_parity(&sm.w1_bar, 0);   // fc1 weights have landed (no-op after the first chunk)
     __syncthreads();
 
     // ---- fc1 -------------------------------------------------------------------------------
