@@ -74,6 +74,8 @@ static consensus::Common<T> common_from(const py::dict& d) {
   c.rho = ptr<const T>(d, "rho"); c.lr = ptr<const T>(d, "lr"); c.alpha = ptr<const T>(d, "alpha");
   c.graph_id = ptr<const int>(d, "graph_id");
   c.calls = ptr<int>(d, "calls");
+  c.loss_part = ptr<const float>(d, "loss_part"); c.tloss = ptr<float>(d, "tloss");
+  c.tdecay = (float)getf(d, "tdecay", 0.0); c.loss_S = geti(d, "loss_S", 1);
   c.flags = ptr<int>(d, "flags"); c.peer_flag = ptr<const int64_t>(d, "peer_flag");
   c.world = geti(d, "world", 1); c.rank = geti(d, "rank", 0);
   c.done_ctr = ptr<unsigned int>(d, "done_ctr"); c.err = ptr<int>(d, "err");

@@ -189,6 +189,21 @@ NNDT_DEVINL Pack<T> sum_partials(const Common<T>& c, int l, int i) {
   return g;
 }
 
+// step bookkeeping done by one thread per node in the kernel that consumes a gradient: advance the sampler's
+// draw counter and fold the step's training loss into the moving average (problems/dist_online_dense_problem.py:129-137)
+template <typename T>
+NNDT_DEVINL void step_bookkeeping(const Common<T>& c, int l) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (c.calls != nullptr) c.calls[l] += 1;
+    if (c.tloss != nullptr) {
+      float loss = 0.f;
+      for (int s = 0; s < c.loss_S; ++s) loss += c.loss_part[l * c.loss_S + s];
+      const float t = c.tloss[l];
+      c.tloss[l] = t != 0.f ? (1.f - c.tdecay) * t + c.tdecay * loss : loss;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ DiNNO ----
 template <typename T>
 __global__ void __launch_bounds__(THREADS) dinno_update_kernel(const DinnoArgs<T> a) {
@@ -276,7 +291,7 @@ __global__ void __launch_bounds__(THREADS) dinno_update_kernel(const DinnoArgs<T
     if (last) stv(pub_row(c, ri.par ^ 1, 0, l) + i, th);
   }
   if (!waited) { pdl_wait(); pdl_launch_dependents(); }
-  if (c.calls != nullptr && blockIdx.x == 0 && threadIdx.x == 0) c.calls[l] += 1;
+  step_bookkeeping(c, l);
   if (last) finish_round(c, ri.k);
 }
 
@@ -332,7 +347,7 @@ __global__ void __launch_bounds__(THREADS) dsgd_step_kernel(const Common<T> c) {
     stv(c.theta + row + i, th);
     stv(pub_row(c, ri.par ^ 1, 0, l) + i, th);
   }
-  if (c.calls != nullptr && blockIdx.x == 0 && threadIdx.x == 0) c.calls[l] += 1;
+  step_bookkeeping(c, l);
   finish_round(c, ri.k);
 }
 
@@ -351,7 +366,7 @@ __global__ void __launch_bounds__(THREADS) dsgt_init_kernel(const DsgtArgs<T> a)
     stv(a.g_old + row + i, g);
     stv(pub_row(c, 0, 1, l) + i, g);
   }
-  if (c.calls != nullptr && blockIdx.x == 0 && threadIdx.x == 0) c.calls[l] += 1;
+  step_bookkeeping(c, l);
 }
 
 template <typename T>
@@ -431,7 +446,7 @@ __global__ void __launch_bounds__(THREADS) dsgt_track_kernel(const DsgtArgs<T> a
     stv(pub_row(c, ri.par ^ 1, 1, l) + i, y);
     stv(pub_row(c, ri.par ^ 1, 0, l) + i, ldv(c.theta + row + i));
   }
-  if (c.calls != nullptr && blockIdx.x == 0 && threadIdx.x == 0) c.calls[l] += 1;
+  step_bookkeeping(c, l);
   finish_round(c, ri.k);
 }
 

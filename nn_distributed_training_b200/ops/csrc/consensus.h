@@ -37,6 +37,10 @@ struct Common {
   const int* graph_id;        // [oits]
   // sampler bookkeeping
   int* calls;                 // [L] or nullptr
+  // optional device-side moving average of the training loss (online density metric, tloss_decay)
+  const float* loss_part;     // [L, loss_S] per-CTA loss partials of the forward/backward kernel
+  float* tloss;               // [L] tracker, nullptr = off
+  float tdecay; int loss_S;
   // cross-GPU sync (nullptr / 0 when single GPU)
   int* flags;                 // [world] local slots written by peers (round published)
   const int64_t* peer_flag;   // [world] address of *their* slot for this rank

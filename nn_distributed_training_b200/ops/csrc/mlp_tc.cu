@@ -44,9 +44,10 @@ struct FwdSmem {
 };
 
 // stage a [64 x K] fp32 weight matrix (row-major, K multiple of 64) as K/64 bf16 swizzled slabs
+template <int TN>
 NNDT_DEVINL void stage_weight(uint8_t* dst, const float* w, int K, int tid) {
   const int chunks = HID * (K / 8);            // 16-byte chunks
-  for (int o = tid; o < chunks; o += NT) {
+  for (int o = tid; o < chunks; o += TN) {
     const int n = o / (K / 8), c = o - n * (K / 8);
     const float4 lo = *reinterpret_cast<const float4*>(w + (size_t)n * K + 8 * c);
     const float4 hi = *reinterpret_cast<const float4*>(w + (size_t)n * K + 8 * c + 4);
@@ -56,13 +57,13 @@ NNDT_DEVINL void stage_weight(uint8_t* dst, const float* w, int K, int tid) {
   }
 }
 
-template <int H1, class S>
+template <int H1, int TN, class S>
 NNDT_DEVINL void stage_all_weights(S& sm, const Args& a, const float* th, int tid) {
-  stage_weight(sm.w1, th + a.off[2], H1, tid);
-  stage_weight(sm.w2, th + a.off[4], HID, tid);
-  stage_weight(sm.w3, th + a.off[6], HID, tid);
-  for (int o = tid; o < H1 * a.d_in; o += NT) sm.w0[o] = th[a.off[0] + o];
-  for (int o = tid; o < H1; o += NT) sm.b0[o] = th[a.off[1] + o];
+  stage_weight<TN>(sm.w1, th + a.off[2], H1, tid);
+  stage_weight<TN>(sm.w2, th + a.off[4], HID, tid);
+  stage_weight<TN>(sm.w3, th + a.off[6], HID, tid);
+  for (int o = tid; o < H1 * a.d_in; o += TN) sm.w0[o] = th[a.off[0] + o];
+  for (int o = tid; o < H1; o += TN) sm.b0[o] = th[a.off[1] + o];
   if (tid < HID) {
     sm.b1[tid] = th[a.off[3] + tid];
     sm.b2[tid] = th[a.off[5] + tid];
@@ -73,14 +74,14 @@ NNDT_DEVINL void stage_all_weights(S& sm, const Args& a, const float* th, int ti
 }
 
 // first layer on CUDA cores: h1[r][f] = relu(sin(scale * z)) or relu(z), z = x[r] . W0[f] + b0[f]
-template <int H1, int DIN, class S>
+template <int H1, int DIN, int TN, class S>
 NNDT_DEVINL void first_layer(S& sm, const Args& a, int tid) {
   const int r = tid & (TILE - 1);
-  const int half = tid >> 7;                       // 2 thread groups split the features
+  const int half = tid >> 7;                       // TN/128 thread groups split the features
   float x[DIN];
 #pragma unroll
   for (int d = 0; d < DIN; ++d) x[d] = sm.xs[r * MAX_DIN + d];
-  constexpr int CH = H1 / 8 / 2;                   // 16-byte chunks per thread
+  constexpr int CH = H1 / 8 / (TN / TILE);         // 16-byte chunks per thread
   for (int c = 0; c < CH; ++c) {
     const int chunk = half * CH + c;               // global chunk index along the H1 features
     float v[8];
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_forward_kernel(const Args a) {
 
   if (warp == 0) tmem_alloc(&sm.tmem_base, 64);
   if (tid == 32) { mbar_init(&sm.bar, 1); mbar_init_fence(); }
-  stage_all_weights<H1>(sm, a, th, tid);
+  stage_all_weights<H1, NT>(sm, a, th, tid);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_forward_kernel(const Args a) {
       sm.xs[r * MAX_DIN + d] = (row0 + r < a.n_rows) ? a.x[(size_t)(row0 + r) * a.d_in + d] : 0.f;
     }
     __syncthreads();
-    first_layer<H1, DIN>(sm, a, tid);
+    first_layer<H1, DIN, NT>(sm, a, tid);
     fence_async_smem();
     __syncthreads();
 
@@ -248,7 +249,7 @@ struct TrainSmem {
   float loss_acc;
   float xs[TILE * MAX_DIN];
   float ys[TILE];
-  float part[TILE];
+  float part[4 * TILE];
   float dz5[TILE];
   int ridx[TILE];
   alignas(8) uint64_t bar;
@@ -289,12 +290,44 @@ NNDT_DEVINL void gemm_dw(uint32_t tmem_d, const uint8_t* a_slab, const uint8_t* 
     mma_bf16(tmem_d, desc_mnmajor(a0, k, ACT_SLAB), desc_mnmajor(b0, k, ACT_SLAB), idesc, accumulate || k != 0);
 }
 
+constexpr int NTT = 512;       // training CTA: 16 warps = 4 TMEM lane quarters x 4 column groups of 16
+
+// column sums over the 32 lanes of a warp of 16 per-lane values: lane j (and j+16) returns column j
+NNDT_DEVINL float colsum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
+#pragma unroll
+  for (int o = 8; o >= 1; o >>= 1) {
+    const bool hi = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = hi ? v[i] : v[i + o];
+      const float keep = hi ? v[i + o] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
+
+// hidden-layer epilogue for a 16-column slice: h = relu(acc + bias) -> two 16-byte chunks of the bf16 slab
+NNDT_DEVINL void hidden_epilogue16(uint32_t tmem_d, uint32_t lane_addr, int cg, int row, const float* bias, uint8_t* dst,
+                                   float (&v)[16]) {
+  tmem_ld16(tmem_d + lane_addr + cg * 16, v);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + bias[cg * 16 + i], 0.f);
+  if (dst != nullptr) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+      *reinterpret_cast<uint4*>(dst + swz_chunk_off(row, cg * 2 + c)) = pack_bf16x8(v + 8 * c);
+  }
+}
+
 template <int H1, int DIN>
-__global__ void __launch_bounds__(NT, 1) mlp_train_kernel(const Args a) {
+__global__ void __launch_bounds__(NTT, 1) mlp_train_kernel(const Args a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   TrainSmem<H1>& sm = *reinterpret_cast<TrainSmem<H1>*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int colhalf = warp >> 2, row = (warp & 3) * 32 + lane;
+  const int cg = warp >> 2, row = (warp & 3) * 32 + lane;      // column group 0..3, batch row of the tile
   const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
   constexpr int NBLK1 = (H1 + 127) / 128;       // 128-feature blocks of the first hidden layer
   constexpr int NH = H1 > 128 ? 128 : H1;        // dH1 is produced NH columns at a time
@@ -335,29 +368,28 @@ __global__ void __launch_bounds__(NT, 1) mlp_train_kernel(const Args a) {
         const int slot = c - cf;       // this CTA's slot among the CTAs that cover node `cur`
         float* gp = a.grad_part + ((size_t)cur * a.S + slot) * a.n_pad;
         fence_after_sync();
-        float v[32];
+        float w[16];
         // dW3, dW2: lanes 0..63 = output feature n, columns = input feature k
         for (int q = 0; q < 2; ++q) {
-          tmem_ld32((q == 0 ? T_DW3 : T_DW2) + lane_addr + colhalf * 32, v);
+          tmem_ld16((q == 0 ? T_DW3 : T_DW2) + lane_addr + cg * 16, w);
           if (row < HID) {
-            float4* dst = reinterpret_cast<float4*>(gp + (q == 0 ? a.off[6] : a.off[4]) + row * HID + colhalf * 32);
+            float4* dst = reinterpret_cast<float4*>(gp + (q == 0 ? a.off[6] : a.off[4]) + row * HID + cg * 16);
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              dst[i] = have_acc ? make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < 4; ++i)
+              dst[i] = have_acc ? make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
         // dW1^T blocks: lane = input feature k (within the 128-block), column = output feature n
         for (int blk = 0; blk < NBLK1; ++blk) {
-          tmem_ld32(T_DW1 + blk * 64 + lane_addr + colhalf * 32, v);
+          tmem_ld16(T_DW1 + blk * 64 + lane_addr + cg * 16, w);
           const int k = blk * 128 + row;
           if (k < H1) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) gp[a.off[2] + (colhalf * 32 + i) * H1 + k] = have_acc ? v[i] : 0.f;
+            for (int i = 0; i < 16; ++i) gp[a.off[2] + (cg * 16 + i) * H1 + k] = have_acc ? w[i] : 0.f;
           }
         }
         // 16-column blocks: [dW0 | db0] (lane = first-layer feature) and the hidden bias sums (lane = feature)
-        if (colhalf == 0) {
-          float w[16];
+        if (cg == 0) {
           for (int blk = 0; blk < NBLK1; ++blk) {
             tmem_ld16(T_DW0 + blk * 16 + lane_addr, w);
             const int f = blk * 128 + row;
@@ -382,7 +414,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_train_kernel(const Args a) {
       cur = l;
       have_acc = false;
       const float* th = a.theta + (size_t)l * a.n_pad;
-      stage_all_weights<H1>(sm, a, th, tid);
+      stage_all_weights<H1, NTT>(sm, a, th, tid);
       if (tid < HID) sm.g_w4[tid] = 0.f;
       if (tid == 0) { sm.g_b4 = 0.f; sm.loss_acc = 0.f; }
       if (a.direct) {
@@ -409,6 +441,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_train_kernel(const Args a) {
     // ---- gather the tile's rows (overlaps the previous tile's last MMAs) ---------------------------
     int my_idx = -1;
     float my_x[DIN];
+    float my_y = 0.f;
     if (tid < TILE) {
       const uint32_t t = t0 + tid;
       if (t < bs) {
@@ -429,8 +462,8 @@ __global__ void __launch_bounds__(NT, 1) mlp_train_kernel(const Args a) {
       }
 #pragma unroll
       for (int d = 0; d < DIN; ++d) my_x[d] = my_idx >= 0 ? a.x[(size_t)my_idx * DIN + d] : 0.f;
+      my_y = my_idx >= 0 ? a.y[my_idx] : 0.f;
     }
-    const float my_y = (tid < TILE && my_idx >= 0) ? a.y[my_idx] : 0.f;
     if (pending) { mbar_wait(&sm.bar, phase); phase ^= 1; pending = false; }   // xa / h1 are free again
     if (tid < TILE) {
       sm.ridx[tid] = my_idx;
@@ -445,39 +478,39 @@ __global__ void __launch_bounds__(NT, 1) mlp_train_kernel(const Args a) {
       *reinterpret_cast<uint4*>(sm.xa + swz_chunk_off(tid, 1)) = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
-    first_layer<H1, DIN>(sm, a, tid);
+    first_layer<H1, DIN, NTT>(sm, a, tid);
     fence_async_smem();
     __syncthreads();
 
-    float v[32];
+    float v[16];
     // ======================= forward ===============================================================
-    if (tid == 0) { fence_after_sync(); gemm_kmajor(T_SCR, sm.h1, sm.w1, H1 / 64, false); commit(&sm.bar); }
+    if (warp == 0 && lane == 0) { fence_after_sync(); gemm_kmajor(T_SCR, sm.h1, sm.w1, H1 / 64, false); commit(&sm.bar); }
     mbar_wait(&sm.bar, phase); phase ^= 1;
     fence_after_sync();
-    hidden_epilogue(T_SCR, sm.b1, sm.h2, warp, lane, v);
+    hidden_epilogue16(T_SCR, lane_addr, cg, row, sm.b1, sm.h2, v);
     fence_before_sync(); fence_async_smem();
     __syncthreads();
-    if (tid == 0) { fence_after_sync(); gemm_kmajor(T_SCR, sm.h2, sm.w2, 1, false); commit(&sm.bar); }
+    if (warp == 0 && lane == 0) { fence_after_sync(); gemm_kmajor(T_SCR, sm.h2, sm.w2, 1, false); commit(&sm.bar); }
     mbar_wait(&sm.bar, phase); phase ^= 1;
     fence_after_sync();
-    hidden_epilogue(T_SCR, sm.b2, sm.h3, warp, lane, v);
+    hidden_epilogue16(T_SCR, lane_addr, cg, row, sm.b2, sm.h3, v);
     fence_before_sync(); fence_async_smem();
     __syncthreads();
-    if (tid == 0) { fence_after_sync(); gemm_kmajor(T_SCR, sm.h3, sm.w3, 1, false); commit(&sm.bar); }
+    if (warp == 0 && lane == 0) { fence_after_sync(); gemm_kmajor(T_SCR, sm.h3, sm.w3, 1, false); commit(&sm.bar); }
     mbar_wait(&sm.bar, phase); phase ^= 1;
     fence_after_sync();
-    hidden_epilogue(T_SCR, sm.b3, nullptr, warp, lane, v);     // v = h4[row][colhalf*32 ..]
+    hidden_epilogue16(T_SCR, lane_addr, cg, row, sm.b3, nullptr, v);     // v = h4[row][cg*16 ..]
     fence_before_sync();
     // ---- output layer, loss, dL/dz5 --------------------------------------------------------------------
     {
       float dot = 0.f;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) dot = fmaf(v[i], sm.w4[colhalf * 32 + i], dot);
-      if (colhalf == 1) sm.part[row] = dot;
+      for (int i = 0; i < 16; ++i) dot = fmaf(v[i], sm.w4[cg * 16 + i], dot);
+      sm.part[cg * TILE + row] = dot;
       __syncthreads();
-      if (colhalf == 0) {
+      if (cg == 0) {
         const bool valid = sm.ridx[row] >= 0;
-        const float z = dot + sm.part[row] + sm.b4;
+        const float z = sm.part[row] + sm.part[TILE + row] + sm.part[2 * TILE + row] + sm.part[3 * TILE + row] + sm.b4;
         const float y = sm.ys[row];
         float p = z, dpdz = 1.f;
         if (a.last_act == kLastSigmoid) { p = 1.f / (1.f + __expf(-z)); dpdz = p * (1.f - p); }
@@ -501,21 +534,22 @@ __global__ void __launch_bounds__(NT, 1) mlp_train_kernel(const Args a) {
     {
       // layer 5 -> dz4 = dz5 * w4 * relu'(h4);  dW4 += dz5 * h4 (the one remaining shuffle reduction)
       const float d5 = sm.dz5[row];
-      float t1[32];
+      float t1[16];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
+      for (int i = 0; i < 16; ++i) {
         t1[i] = d5 * v[i];
-        v[i] = v[i] > 0.f ? d5 * sm.w4[colhalf * 32 + i] : 0.f;
+        v[i] = v[i] > 0.f ? d5 * sm.w4[cg * 16 + i] : 0.f;
       }
 #pragma unroll
-      for (int cch = 0; cch < 4; ++cch)
-        *reinterpret_cast<uint4*>(sm.dz + swz_chunk_off(row, colhalf * 4 + cch)) = pack_bf16x8(v + 8 * cch);
-      atomicAdd(&sm.g_w4[colhalf * 32 + lane], colsum32(t1, lane));
+      for (int cch = 0; cch < 2; ++cch)
+        *reinterpret_cast<uint4*>(sm.dz + swz_chunk_off(row, cg * 2 + cch)) = pack_bf16x8(v + 8 * cch);
+      const float s4 = colsum16(t1, lane);
+      if (lane < 16) atomicAdd(&sm.g_w4[cg * 16 + lane], s4);
     }
     fence_async_smem();
     __syncthreads();
     // dh3 = dz4 . W3 ; dW3 += dz4^T . h3 ; db3 += dz4^T . [x,1]
-    if (tid == 0) {
+    if (warp == 0 && lane == 0) {
       fence_after_sync();
       gemm_dh<64>(T_SCR, sm.dz, sm.w3);
       gemm_dw<64>(T_DW3, sm.dz, sm.h3, have_acc);
@@ -528,21 +562,21 @@ __global__ void __launch_bounds__(NT, 1) mlp_train_kernel(const Args a) {
     for (int layer = 3; layer >= 2; --layer) {
       // dz_{layer} = dh_{layer} * relu'(h_{layer})
       const uint8_t* hs = layer == 3 ? sm.h3 : sm.h2;
-      tmem_ld32(T_SCR + lane_addr + colhalf * 32, v);
+      tmem_ld16(T_SCR + lane_addr + cg * 16, v);
       fence_before_sync();
 #pragma unroll
-      for (int cch = 0; cch < 4; ++cch) {
-        const uint4 hv = *reinterpret_cast<const uint4*>(hs + swz_chunk_off(row, colhalf * 4 + cch));
+      for (int cch = 0; cch < 2; ++cch) {
+        const uint4 hv = *reinterpret_cast<const uint4*>(hs + swz_chunk_off(row, cg * 2 + cch));
         const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&hv);
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[cch * 8 + e] = __bfloat162float(hb[e]) > 0.f ? v[cch * 8 + e] : 0.f;
       }
 #pragma unroll
-      for (int cch = 0; cch < 4; ++cch)
-        *reinterpret_cast<uint4*>(sm.dz + swz_chunk_off(row, colhalf * 4 + cch)) = pack_bf16x8(v + 8 * cch);
+      for (int cch = 0; cch < 2; ++cch)
+        *reinterpret_cast<uint4*>(sm.dz + swz_chunk_off(row, cg * 2 + cch)) = pack_bf16x8(v + 8 * cch);
       fence_async_smem();
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0 && lane == 0) {
         fence_after_sync();
         if (layer == 3) {
           gemm_dh<64>(T_SCR, sm.dz, sm.w2);
@@ -565,21 +599,25 @@ __global__ void __launch_bounds__(NT, 1) mlp_train_kernel(const Args a) {
       float x[DIN];
 #pragma unroll
       for (int d = 0; d < DIN; ++d) x[d] = sm.xs[row * MAX_DIN + d];
+      constexpr int CPT = NH / 4;              // columns per thread per half (4 column groups)
 #pragma unroll 1
       for (int half = 0; half < (H1 + NH - 1) / NH; ++half) {
         if (half > 0) {
           fence_before_sync();
           __syncthreads();
-          if (tid == 0) { fence_after_sync(); gemm_dh<NH>(T_SCR, sm.dz, sm.w1 + half * (NH / 64) * W_SLAB); commit(&sm.bar); }
+          if (warp == 0 && lane == 0) {
+            fence_after_sync(); gemm_dh<NH>(T_SCR, sm.dz, sm.w1 + half * (NH / 64) * W_SLAB); commit(&sm.bar);
+          }
           mbar_wait(&sm.bar, phase); phase ^= 1;
           fence_after_sync();
         }
 #pragma unroll 1
-        for (int q = 0; q < NH / 64; ++q) {
-          const int f0 = half * NH + (q * 2 + colhalf) * 32;     // this thread's 32 features
-          tmem_ld32(T_SCR + lane_addr + (q * 2 + colhalf) * 32, v);
+        for (int q = 0; q < CPT / 16; ++q) {
+          const int col = cg * CPT + q * 16;           // column inside the NH-wide scratch
+          const int f0 = half * NH + col;              // first-layer feature of v[0]
+          tmem_ld16(T_SCR + lane_addr + col, v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
+          for (int i = 0; i < 16; ++i) {
             const int f = f0 + i;
             float z = sm.b0[f];
 #pragma unroll
@@ -597,14 +635,14 @@ __global__ void __launch_bounds__(NT, 1) mlp_train_kernel(const Args a) {
           const int chunk0 = (f0 & 63) >> 3;
           uint8_t* slab = sm.h1 + (f0 >> 6) * ACT_SLAB;
 #pragma unroll
-          for (int cch = 0; cch < 4; ++cch)
+          for (int cch = 0; cch < 2; ++cch)
             *reinterpret_cast<uint4*>(slab + swz_chunk_off(row, chunk0 + cch)) = pack_bf16x8(v + 8 * cch);
         }
       }
       fence_before_sync();
       fence_async_smem();
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0 && lane == 0) {
         fence_after_sync();
         for (int blk = 0; blk < NBLK1; ++blk)
           gemm_dw<16>(T_DW0 + blk * 16, sm.h1 + blk * 2 * ACT_SLAB, sm.xa, have_acc);
@@ -625,7 +663,7 @@ static cudaError_t launch_train_t(const Args& a, int ctas, cudaStream_t st) {
   static cudaError_t attr = cudaFuncSetAttribute(mlp_train_kernel<H1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (attr != cudaSuccess) return attr;
   if (a.d_in != 2) return cudaErrorInvalidValue;
-  mlp_train_kernel<H1, 2><<<dim3(ctas), NT, smem, st>>>(a);
+  mlp_train_kernel<H1, 2><<<dim3(ctas), NTT, smem, st>>>(a);
   return cudaGetLastError();
 }
 

@@ -146,6 +146,11 @@ class ConsensusEngine:
         # published buffer is allocated with the max count, so pass that as the row count of pub
         d["L"] = L
         d["pub_L"] = self.Lpub
+        if pr.fused is not None and getattr(pr, "track_tloss", False) and self.dtype == torch.float32:
+            # the kernel that consumes a gradient also folds that step's loss into the EMA tracker
+            d.update(loss_part=pr.fused.loss_part.data_ptr(), tloss=pr.tloss_local.data_ptr(),
+                     tdecay=float(pr.tloss_decay), loss_S=int(pr.fused.loss_part.shape[1]))
+            pr.fused.ema_in_kernel = True
         if self.sum_mode:
             d.update(sum_mode=1, n_total=pr.N, sum_local=self.sum_buf.local.data_ptr(), sum_mc=sum_mc,
                      sum_flags=self.sum_flag_buf.local.data_ptr(), peer_sum_flag=self.t_peer_sum_flag.data_ptr())

@@ -118,9 +118,11 @@ class FusedMLP:
             tab[l, 2 + 2 * K + 1: 2 + 2 * K + 1 + len(wins)] = [w[1] for w in wins]
         return torch.as_tensor(tab, device=pr.device)
 
+    ema_in_kernel = False   # set by the consensus engine when its kernels maintain the loss EMA
+
     def launch(self):
         self.train_op.train()
-        if getattr(self.pr, "track_tloss", False):
+        if getattr(self.pr, "track_tloss", False) and not self.ema_in_kernel:
             # device-side EMA of the training loss (capturable: no host sync)
             self.pr._ema_update(self.pr.tloss_local, self.loss_part.sum(1))
 
@@ -131,6 +133,8 @@ class FusedMLP:
         self.calls += 1
         pr.count_draws_all(1)
         pr.last_losses = self.loss_part.sum(1)
+        if getattr(pr, "track_tloss", False) and self.ema_in_kernel:
+            pr._ema_update(pr.tloss_local, pr.last_losses)   # eager API: no consensus kernel follows
         return pr.last_losses
 
     def sync_calls_from_host(self):
