@@ -222,3 +222,35 @@ def test_link_drop_fault_injection_changes_graph_and_training_survives():
     assert torch.isfinite(pr.arena.theta).all()
     # the eager path walked the same graph sequence as the plan
     assert pr._graph_round == 5
+
+
+def test_lidar_matches_reference_scans():
+    """Vectorised lidar vs the reference's per-beam Python loops on the reference's own floor plan."""
+    import importlib.util, os
+    ref_py = "/root/reference/floorplans/lidar/lidar.py"
+    img = "/root/reference/floorplans/32_data/floor_img.png"
+    if not (os.path.exists(ref_py) and os.path.exists(img)):
+        pytest.skip("reference floor plan not mounted")
+    spec = importlib.util.spec_from_file_location("reflidar", ref_py)
+    ref = importlib.util.module_from_spec(spec); spec.loader.exec_module(ref)
+    from nn_distributed_training_b200.floorplans.lidar import ClippedLidar2D, Lidar2D, interpolate_waypoints
+    args = (img, 12, 0.2, 15, 1.0, 30, 3)
+    mine, theirs = Lidar2D(*args, border_width=30), ref.Lidar2D(*args, border_width=30)
+    wp = np.load("/root/reference/floorplans/32_data/tight_paths/1.npy")
+    np.testing.assert_allclose(interpolate_waypoints(wp[:, 0], wp[:, 1], 3), ref.interpolate_waypoints(wp[:, 0], wp[:, 1], 3))
+    traj = interpolate_waypoints(wp[:, 0], wp[:, 1], 1)[::6] * np.array([mine.nx * 0.5, mine.ny * 0.5])
+    a = mine.scan_batch(traj)
+    b = np.stack([theirs.scan(p.reshape(1, 2)) for p in traj])
+    np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-9)
+    cm, ct = ClippedLidar2D(img, 12, 0.2, 15, border_width=30), ref.ClippedLidar2D(img, 12, 0.2, 15, border_width=30)
+    for p in traj[:4]:
+        np.testing.assert_allclose(cm.scan(p.reshape(1, 2)), ct.scan(p.reshape(1, 2)), rtol=1e-9, atol=1e-9)
+
+
+def test_round_timer_as_profiler_hook():
+    from nn_distributed_training_b200.utils.timing import RoundTimer
+    conf = {"alg_name": "dsgd", "alpha0": 0.05, "mu": 0.0, "outer_iterations": 6, "profile": False}
+    pr = _mnist_problem(3, nx.cycle_graph(3), conf)
+    t = RoundTimer(warmup=2)
+    DSGD(pr, "cpu", conf).train(profiler=t)
+    assert t.ms_per_round() is not None and t.ms_per_round() > 0
