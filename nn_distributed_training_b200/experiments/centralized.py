@@ -70,7 +70,7 @@ def centralized_density(yaml_pth, online=True):
     ctx = common.make_context(conf)
     data_conf = conf["data"]
     data_dir = dc.resolve_data_dir(data_conf, ctx)
-    lidar = dc.make_lidar(data_conf, data_dir)
+    lidar = dc.make_lidar(data_conf, data_dir, device=ctx.device)
     paths = dc.waypoint_files(data_dir, data_conf["waypoint_subdir"])
     sets = [TrajectoryLidarDataset(lidar, np.load(p), data_conf["spline_res"], round_density=data_conf["round_density"]) for p in paths]
     train = Shard(torch.cat([s.shard.x for s in sets]), torch.cat([s.shard.y for s in sets]))

@@ -31,7 +31,19 @@ def resolve_data_dir(data_conf, ctx) -> str:
     return out
 
 
-def make_lidar(data_conf, data_dir, clipped=False):
+def make_lidar(data_conf, data_dir, clipped=False, device=None):
+    """``device``: a CUDA device makes ``Lidar2D`` generate its scans with ops/csrc/lidar.cu
+    (``data_conf['lidar_backend']``: auto | cuda | numpy)."""
+    lidar = _make_lidar(data_conf, data_dir, clipped)
+    backend = str(data_conf.get("lidar_backend", "auto"))
+    if backend != "numpy" and not clipped and device is not None and torch.device(device).type == "cuda":
+        from ..ops import fused_available
+        if fused_available() or backend == "cuda":
+            lidar.scan_device = torch.device(device)
+    return lidar
+
+
+def _make_lidar(data_conf, data_dir, clipped=False):
     img_path = os.path.join(data_dir, "floor_img.png")
     if clipped:
         return ClippedLidar2D(img_path, data_conf["num_beams"], data_conf["beam_length"], data_conf["beam_samps"],

@@ -35,7 +35,7 @@ def experiment(yaml_pth):
     if ctx.is_main:
         print("Loading the data ...")
     data_dir = dc.resolve_data_dir(data_conf, ctx)
-    lidar = dc.make_lidar(data_conf, data_dir, clipped=bool(data_conf.get("clipped_lidar", False)))
+    lidar = dc.make_lidar(data_conf, data_dir, clipped=bool(data_conf.get("clipped_lidar", False)), device=ctx.device)
     if data_conf["split_type"] == "random":
         train_subsets = [RandomPoseLidarDataset(lidar, data_conf["num_scans"], round_density=data_conf["round_density"])
                          for _ in range(N)]

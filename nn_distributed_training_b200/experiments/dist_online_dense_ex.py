@@ -29,7 +29,7 @@ def experiment(yaml_pth):
     if ctx.is_main:
         print("Loading the data ...")
     data_dir = dc.resolve_data_dir(data_conf, ctx)
-    lidar = dc.make_lidar(data_conf, data_dir)
+    lidar = dc.make_lidar(data_conf, data_dir, device=ctx.device)
     paths = dc.waypoint_files(data_dir, data_conf["waypoint_subdir"])
     N = int(data_conf.get("num_nodes", len(paths)))   # reference: one node per waypoint file (:136-139)
     if N > len(paths) or N == 0:

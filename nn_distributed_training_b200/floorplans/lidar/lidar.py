@@ -79,8 +79,38 @@ class Lidar2D(_LidarBase):
         self.samp_df = samp_distribution_factor
         self._setup_grid(img_dir, border_width, beam_length)
 
-    def scan_batch(self, pos, chunk=512):
-        """All beams of all poses ``pos [P,2]`` -> ``[P, num_beams*beam_samps, 3]``."""
+    def _spline_tables(self, device):
+        """Knots / coefficients of the fitted bicubic spline on ``device`` (for ops/csrc/lidar.cu)."""
+        key = str(device)
+        if getattr(self, "_tables", None) is None or self._tables[0] != key:
+            tx, ty = self.density.get_knots()
+            c = self.density.get_coeffs()
+            t = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=device)
+            self._tables = (key, t(tx), t(ty), t(c))
+        return self._tables[1:]
+
+    def scan_batch_cuda(self, pos, device="cuda"):
+        """GPU twin of ``scan_batch`` (one thread per pose x beam; fp64)."""
+        from ...ops import load_ext
+        ext = load_ext(required=True)
+        pos = np.asarray(pos, dtype=float).reshape(-1, 2)
+        self._check_free(pos)
+        tx, ty, c = self._spline_tables(device)
+        poses = torch.as_tensor(pos, dtype=torch.float64, device=device).contiguous()
+        out = torch.empty(pos.shape[0], self.num_beams * self.beam_samps, 3, dtype=torch.float64, device=device)
+        ext.lidar_scan(dict(tx=tx.data_ptr(), ty=ty.data_ptr(), coef=c.data_ptr(), ntx=tx.numel(), nty=ty.numel(),
+                            poses=poses.data_ptr(), n_poses=pos.shape[0], num_beams=self.num_beams,
+                            beam_samps=self.beam_samps, collision_samps=self.collision_samps,
+                            fine_samps=self.fine_samps, beam_len=float(self.beam_len), samp_df=float(self.samp_df),
+                            out=out.data_ptr()))
+        return out
+
+    def scan_batch(self, pos, chunk=512, device=None):
+        """All beams of all poses ``pos [P,2]`` -> ``[P, num_beams*beam_samps, 3]``.  With a CUDA
+        ``device`` the scans are generated by the GPU kernel and returned as a NumPy array."""
+        device = device if device is not None else getattr(self, "scan_device", None)
+        if device is not None and torch.device(device).type == "cuda":
+            return self.scan_batch_cuda(pos, device).cpu().numpy()
         pos = np.asarray(pos, dtype=float).reshape(-1, 2)
         self._check_free(pos)
         out = np.empty((pos.shape[0], self.num_beams * self.beam_samps, 3))

@@ -5,6 +5,7 @@
 #include <pybind11/stl.h>
 
 #include "mlp.h"
+#include "lidar.h"
 
 namespace py = pybind11;
 using namespace nndt;
@@ -44,7 +45,26 @@ struct MlpOp {
 };
 }  // namespace
 
+static lidar::Args lidar_args(const py::dict& d) {
+  lidar::Args a{};
+  a.tx = ptr<const double>(d, "tx"); a.ty = ptr<const double>(d, "ty"); a.coef = ptr<const double>(d, "coef");
+  a.ntx = geti(d, "ntx"); a.nty = geti(d, "nty");
+  a.poses = ptr<const double>(d, "poses"); a.n_poses = geti(d, "n_poses");
+  a.num_beams = geti(d, "num_beams"); a.beam_samps = geti(d, "beam_samps");
+  a.collision_samps = geti(d, "collision_samps"); a.fine_samps = geti(d, "fine_samps");
+  a.beam_len = getf(d, "beam_len"); a.samp_df = getf(d, "samp_df", 1.0);
+  a.out = ptr<double>(d, "out");
+  return a;
+}
+
 void bind_mlp(py::module& m) {
+  m.def("lidar_scan", [](const py::dict& d) {
+    check(lidar::launch_scan(lidar_args(d), at::cuda::getCurrentCUDAStream().stream()), "lidar_scan");
+  });
+  m.def("lidar_density", [](const py::dict& d, uint64_t xy, int n, uint64_t out) {
+    check(lidar::launch_density(lidar_args(d), reinterpret_cast<const double*>(xy), n, reinterpret_cast<double*>(out),
+                                at::cuda::getCurrentCUDAStream().stream()), "lidar_density");
+  });
   py::class_<MlpOp>(m, "MlpOp")
       .def(py::init<const py::dict&>())
       .def("update", &MlpOp::update)

@@ -164,7 +164,7 @@ __device__ __forceinline__ void fc1_forward(Smem<SPB, NT>& sm, int tid) {
   for (int s = 0; s < SPB; ++s) acc[s] = 0.f;
   const float4* wrow = reinterpret_cast<const float4*>(sm.w1 + j * W1_STRIDE) + ks * K4S;
   const float4* arow = reinterpret_cast<const float4*>(sm.a1) + ks * K4S;
-#pragma unroll 3
+#pragma unroll
   for (int i = 0; i < K4S; ++i) {
     const float4 w = wrow[i];
 #pragma unroll
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(NT, 1) mnist_kernel(const Args a) {
       float acc[SPB];
 #pragma unroll
       for (int s = 0; s < SPB; ++s) acc[s] = 0.f;
-#pragma unroll 4
+#pragma unroll 8
       for (int j = 0; j < HID; ++j) {
         const float w = sm.w1[j * W1_STRIDE + tid];
 #pragma unroll

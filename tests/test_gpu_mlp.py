@@ -139,3 +139,20 @@ def test_online_density_fused_training_tracks_torch_path(tmp_path):
     tf, tr = fused.metrics["train_loss_moving_average"][-1], ref.metrics["train_loss_moving_average"][-1]
     torch.testing.assert_close(tf, tr, rtol=5e-2, atol=2e-2)
     assert fused.forward_cnt == ref.forward_cnt
+
+
+def test_gpu_lidar_matches_cpu_scans(tmp_path):
+    """ops/csrc/lidar.cu (bicubic B-spline density + beam marching, fp64) vs the NumPy/scipy path."""
+    import os
+    import numpy as np
+    from nn_distributed_training_b200.floorplans.lidar import Lidar2D, interpolate_waypoints
+    from nn_distributed_training_b200.floorplans.synthetic import write_dataset
+    d = str(tmp_path)
+    write_dataset(d, n_paths=2, seed=1)
+    lidar = Lidar2D(os.path.join(d, "floor_img.png"), 20, 0.2, 25, 1.3, 50, 3, border_width=8)
+    wp = np.load(os.path.join(d, "tight_paths", "1.npy"))
+    traj = interpolate_waypoints(wp[:, 0], wp[:, 1], 6) * np.array([lidar.nx * 0.5, lidar.ny * 0.5])
+    cpu = lidar.scan_batch(traj)
+    gpu = lidar.scan_batch(traj, device=DEV)
+    assert gpu.shape == cpu.shape
+    np.testing.assert_allclose(gpu, cpu, rtol=0, atol=1e-7)
