@@ -8,6 +8,7 @@
 
 #include "consensus.h"
 #include "mnist.h"
+#include "dinno_round.h"
 
 namespace py = pybind11;
 using namespace nndt;
@@ -122,6 +123,25 @@ static void bind_consensus(py::module& m, const char* name) {
       .def("dsgt_track", &ConsensusOp<T>::dsgt_track);
 }
 
+// One launch per DiNNO round (dinno_round.cu): mnist dict + consensus dict + per-step batch sources
+struct DinnoRoundOp {
+  round::RoundArgs a{};
+  int S = 1;
+  DinnoRoundOp(const py::dict& md, const py::dict& cd, const py::list& steps) {
+    MnistOp mo(md);
+    ConsensusOp<float> co(cd);
+    a.m = mo.a; a.d = co.dn; S = mo.S;
+    a.prof = ptr<long long>(md, "prof");
+    if ((int)steps.size() != a.d.pits || a.d.pits > round::kMaxSteps) throw std::runtime_error("DinnoRoundOp: bad step list");
+    for (int p = 0; p < a.d.pits; ++p) {
+      const py::dict sd = steps[p].cast<py::dict>();
+      a.x_step[p] = ptr<const void>(sd, "x"); a.y_step[p] = ptr<const int64_t>(sd, "y");
+      a.bs_step[p] = ptr<const int>(sd, "direct_bs");
+    }
+  }
+  void launch() { check(round::launch_dinno_round(a, S, cur_stream()), "dinno_round"); }
+};
+
 void bind_mlp(py::module& m);     // mlp_bind.cpp
 void bind_runtime(py::module& m); // runtime.cpp
 
@@ -144,6 +164,10 @@ PYBIND11_MODULE(_C, m) {
     check(f64 ? consensus::launch_consensus_metric<double>(r, N, n_pad, local0, L, a, b, c, cur_stream())
               : consensus::launch_consensus_metric<float>(r, N, n_pad, local0, L, a, b, c, cur_stream()), "consensus_metric");
   });
+  py::class_<DinnoRoundOp>(m, "DinnoRoundOp")
+      .def(py::init<const py::dict&, const py::dict&, const py::list&>())
+      .def("launch", &DinnoRoundOp::launch);
+  m.def("dinno_round_max_clusters", [](int S) { return round::max_active_clusters(S); });
   bind_consensus<float>(m, "ConsensusOpF32");
   bind_consensus<double>(m, "ConsensusOpF64");
   bind_mlp(m);

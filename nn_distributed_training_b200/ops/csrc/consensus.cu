@@ -16,129 +16,11 @@
 // (st.release.sys over NVLink after __threadfence_system()); consumers spin with
 // ld.acquire.sys on their *local* flag array only for the ranks that own a neighbor.  Since a
 // node publishes k+1 only after finishing its round-k reads, two buffers suffice.
-#include "common.cuh"
-#include "consensus.h"
+#include "consensus_device.cuh"
 
 namespace nndt {
 namespace consensus {
 
-constexpr int THREADS = 256;
-constexpr long long kSpinLimit = 20000000000LL;  // ~10 s at 2 GHz, then flag an error and go on
-
-template <typename T> struct Vec;
-template <> struct Vec<float> { using type = float4; static constexpr int N = 4; };
-template <> struct Vec<double> { using type = double2; static constexpr int N = 2; };
-
-template <typename T> struct Pack { T v[Vec<T>::N]; };
-
-template <typename T>
-NNDT_DEVINL Pack<T> ldv(const T* p) {
-  Pack<T> r;
-  *reinterpret_cast<typename Vec<T>::type*>(r.v) = *reinterpret_cast<const typename Vec<T>::type*>(p);
-  return r;
-}
-template <typename T>
-NNDT_DEVINL void stv(T* p, const Pack<T>& r) {
-  *reinterpret_cast<typename Vec<T>::type*>(p) = *reinterpret_cast<const typename Vec<T>::type*>(r.v);
-}
-
-template <typename T>
-struct RoundInfo { int k, par, gid; };
-
-template <typename T>
-NNDT_DEVINL RoundInfo<T> round_info(const Common<T>& c) {
-  RoundInfo<T> r;
-  r.k = *c.round_ctr;
-  r.par = r.k & 1;
-  r.gid = c.graph_id[r.k];
-  return r;
-}
-
-// wait until every rank owning a neighbor of local node l has published round k
-template <typename T>
-NNDT_DEVINL void wait_neighbors(const Common<T>& c, int gid, int l, int k) {
-  if (c.world > 1) {
-    const int d = c.deg[gid * c.L + l];
-    if ((int)threadIdx.x < d) {
-      const int r = c.nbr_rank[(gid * c.L + l) * c.dmax + threadIdx.x];
-      if (r >= 0) {
-        const long long t0 = clock64();
-        while (ld_acquire_sys(c.flags + r) < k) {
-          if (clock64() - t0 > kSpinLimit) { *c.err = 1; break; }
-        }
-      }
-    }
-    __syncthreads();
-  }
-}
-
-// last block of the launch: advance the round counter and announce the new round to peers
-template <typename T>
-NNDT_DEVINL void finish_round(const Common<T>& c, int k) {
-  __shared__ bool is_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned total = gridDim.x * gridDim.y;
-    is_last = (atomicAdd(c.done_ctr, 1u) == total - 1);
-  }
-  __syncthreads();
-  if (is_last) {
-    if (threadIdx.x == 0) {
-      *c.done_ctr = 0;
-      *c.round_ctr = k + 1;
-    }
-    if (c.world > 1) {
-      __threadfence_system();
-      if ((int)threadIdx.x < c.world && (int)threadIdx.x != c.rank)
-        st_release_sys(reinterpret_cast<int*>(c.peer_flag[threadIdx.x]), k + 1);
-    }
-  }
-}
-
-template <typename T>
-NNDT_DEVINL const T* nbr_row(const Common<T>& c, int gid, int l, int e, int par, int chan) {
-  return reinterpret_cast<const T*>(c.nbr_ptr[(((size_t)(gid * c.L + l) * c.dmax + e) * 2 + par) * c.C + chan]);
-}
-template <typename T>
-NNDT_DEVINL T* pub_row(const Common<T>& c, int par, int chan, int l) {
-  return c.pub + ((size_t)(par * c.C + chan) * c.pub_L + l) * c.n_pad;
-}
-
-// ---- complete-graph mode -----------------------------------------------------------------------
-// network-wide sum of channel `chan` at element i for parity `par`
-template <int N> struct DPack { double v[N]; };
-template <typename T>
-NNDT_DEVINL DPack<Vec<T>::N> network_sum(const Common<T>& c, int par, int chan, int i) {
-  constexpr int N = Vec<T>::N;
-  const size_t off = (size_t)(par * c.C + chan) * c.n_pad + i;
-  DPack<N> r;
-  if (c.sum_mc != nullptr) {
-#pragma unroll
-    for (int u = 0; u < N; ++u)
-      asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f64 %0, [%1];" : "=d"(r.v[u]) : "l"(c.sum_mc + off + u) : "memory");
-  } else {
-#pragma unroll
-    for (int u = 0; u < N; u += 2) {
-      const double2 q = *reinterpret_cast<const double2*>(c.sum_local + off + u);
-      r.v[u] = q.x; r.v[u + 1] = q.y;
-    }
-  }
-  return r;
-}
-// every rank's partial sum of round k must be in place before the in-switch reduction reads it
-template <typename T>
-NNDT_DEVINL void wait_all_sums(const Common<T>& c, int k) {
-  if (c.world > 1) {
-    if ((int)threadIdx.x < c.world && (int)threadIdx.x != c.rank) {
-      const long long t0 = clock64();
-      while (ld_acquire_sys(c.sum_flags + threadIdx.x) < k + 1) {
-        if (clock64() - t0 > kSpinLimit) { *c.err = 1; break; }
-      }
-    }
-    __syncthreads();
-  }
-}
 // S_local[par][chan] = sum over this rank's nodes of the published rows of round k
 template <typename T>
 __global__ void __launch_bounds__(THREADS) local_sum_kernel(const Common<T> c) {
@@ -177,32 +59,6 @@ __global__ void __launch_bounds__(THREADS) local_sum_kernel(const Common<T> c) {
   }
 }
 
-template <typename T>
-NNDT_DEVINL Pack<T> sum_partials(const Common<T>& c, int l, int i) {
-  const T* gp = c.grad_part + (size_t)l * c.S * c.n_pad + i;
-  Pack<T> g = ldv(gp);
-  for (int s = 1; s < c.S; ++s) {
-    const Pack<T> q = ldv(gp + (size_t)s * c.n_pad);
-#pragma unroll
-    for (int u = 0; u < Vec<T>::N; ++u) g.v[u] += q.v[u];
-  }
-  return g;
-}
-
-// step bookkeeping done by one thread per node in the kernel that consumes a gradient: advance the sampler's
-// draw counter and fold the step's training loss into the moving average (problems/dist_online_dense_problem.py:129-137)
-template <typename T>
-NNDT_DEVINL void step_bookkeeping(const Common<T>& c, int l) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    if (c.calls != nullptr) c.calls[l] += 1;
-    if (c.tloss != nullptr) {
-      float loss = 0.f;
-      for (int s = 0; s < c.loss_S; ++s) loss += c.loss_part[l * c.loss_S + s];
-      const float t = c.tloss[l];
-      c.tloss[l] = t != 0.f ? (1.f - c.tdecay) * t + c.tdecay * loss : loss;
-    }
-  }
-}
 
 // ------------------------------------------------------------------ DiNNO ----
 template <typename T>
@@ -212,15 +68,11 @@ __global__ void __launch_bounds__(THREADS) dinno_update_kernel(const DinnoArgs<T
   const int l = blockIdx.y;
   const RoundInfo<T> ri = round_info(c);
   const int deg = c.deg[ri.gid * c.L + l];
-  const T rho = c.rho[ri.k], lr = c.lr[ri.k];
+  const DinnoCoef<T> cf = dinno_coef(a, ri.k, a.step, deg);
+  const T rho = cf.rho;
   const bool first = a.step == 0, last = a.step == a.pits - 1;
   if (first) { if (c.sum_mode) wait_all_sums(c, ri.k); else wait_neighbors(c, ri.gid, l, ri.k); }
 
-  const T b1 = (T)0.9, b2 = (T)0.999, eps = (T)1e-8, wd = (T)1e-2;
-  const int t = a.persistent ? ri.k * a.pits + a.step + 1 : a.step + 1;
-  const T bc1 = (T)1 - pow((T)0.9, (T)t);
-  const T bc2s = sqrt((T)1 - pow((T)0.999, (T)t));
-  const T step_size = lr / bc1;
   const bool fresh = first && !a.persistent;  // Adam moments restart every round (reference Q3)
 
   const size_t row = (size_t)l * c.n_pad;
@@ -269,21 +121,8 @@ __global__ void __launch_bounds__(THREADS) dinno_update_kernel(const DinnoArgs<T
     }
     if (!waited) { pdl_wait(); pdl_launch_dependents(); waited = true; }
     const Pack<T> gl = sum_partials(c, l, i);
-    Pack<T> g;
-#pragma unroll
-    for (int u = 0; u < N; ++u)
-      g.v[u] = gl.v[u] + du.v[u] + (T)2 * rho * (T)deg * (th.v[u] - thk.v[u]) - rho * dl.v[u];
-    if (a.opt == kSGD) {
-#pragma unroll
-      for (int u = 0; u < N; ++u) th.v[u] -= lr * g.v[u];
-    } else {
-#pragma unroll
-      for (int u = 0; u < N; ++u) {
-        if (a.opt == kAdamW) th.v[u] *= ((T)1 - lr * wd);
-        m.v[u] = b1 * m.v[u] + ((T)1 - b1) * g.v[u];
-        v.v[u] = b2 * v.v[u] + ((T)1 - b2) * g.v[u] * g.v[u];
-        th.v[u] -= step_size * m.v[u] / (sqrt(v.v[u]) / bc2s + eps);
-      }
+    dinno_apply(cf, th, thk, dl, du, m, v, gl);
+    if (a.opt != kSGD) {
       stv(a.m + row + i, m);
       stv(a.v + row + i, v);
     }

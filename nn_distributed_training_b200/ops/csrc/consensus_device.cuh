@@ -1,0 +1,208 @@
+// Device-side helpers of the consensus kernels (shared by consensus.cu and dinno_round.cu).
+#pragma once
+#include "common.cuh"
+#include "consensus.h"
+
+namespace nndt {
+namespace consensus {
+
+constexpr int THREADS = 256;
+constexpr long long kSpinLimit = 20000000000LL;  // ~10 s at 2 GHz, then flag an error and go on
+
+template <typename T> struct Vec;
+template <> struct Vec<float> { using type = float4; static constexpr int N = 4; };
+template <> struct Vec<double> { using type = double2; static constexpr int N = 2; };
+
+template <typename T> struct Pack { T v[Vec<T>::N]; };
+
+template <typename T>
+NNDT_DEVINL Pack<T> ldv(const T* p) {
+  Pack<T> r;
+  *reinterpret_cast<typename Vec<T>::type*>(r.v) = *reinterpret_cast<const typename Vec<T>::type*>(p);
+  return r;
+}
+template <typename T>
+NNDT_DEVINL void stv(T* p, const Pack<T>& r) {
+  *reinterpret_cast<typename Vec<T>::type*>(p) = *reinterpret_cast<const typename Vec<T>::type*>(r.v);
+}
+
+template <typename T>
+struct RoundInfo { int k, par, gid; };
+
+template <typename T>
+NNDT_DEVINL RoundInfo<T> round_info(const Common<T>& c) {
+  RoundInfo<T> r;
+  r.k = *c.round_ctr;
+  r.par = r.k & 1;
+  r.gid = c.graph_id[r.k];
+  return r;
+}
+
+// wait until every rank owning a neighbor of local node l has published round k
+template <typename T>
+NNDT_DEVINL void wait_neighbors(const Common<T>& c, int gid, int l, int k) {
+  if (c.world > 1) {
+    const int d = c.deg[gid * c.L + l];
+    if ((int)threadIdx.x < d) {
+      const int r = c.nbr_rank[(gid * c.L + l) * c.dmax + threadIdx.x];
+      if (r >= 0) {
+        const long long t0 = clock64();
+        while (ld_acquire_sys(c.flags + r) < k) {
+          if (clock64() - t0 > kSpinLimit) { *c.err = 1; break; }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// last block of the launch: advance the round counter and announce the new round to peers
+template <typename T>
+NNDT_DEVINL void finish_round(const Common<T>& c, int k) {
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned total = gridDim.x * gridDim.y;
+    is_last = (atomicAdd(c.done_ctr, 1u) == total - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    if (threadIdx.x == 0) {
+      *c.done_ctr = 0;
+      *c.round_ctr = k + 1;
+    }
+    if (c.world > 1) {
+      __threadfence_system();
+      if ((int)threadIdx.x < c.world && (int)threadIdx.x != c.rank)
+        st_release_sys(reinterpret_cast<int*>(c.peer_flag[threadIdx.x]), k + 1);
+    }
+  }
+}
+
+template <typename T>
+NNDT_DEVINL const T* nbr_row(const Common<T>& c, int gid, int l, int e, int par, int chan) {
+  return reinterpret_cast<const T*>(c.nbr_ptr[(((size_t)(gid * c.L + l) * c.dmax + e) * 2 + par) * c.C + chan]);
+}
+template <typename T>
+NNDT_DEVINL T* pub_row(const Common<T>& c, int par, int chan, int l) {
+  return c.pub + ((size_t)(par * c.C + chan) * c.pub_L + l) * c.n_pad;
+}
+
+// ---- complete-graph mode -----------------------------------------------------------------------
+// network-wide sum of channel `chan` at element i for parity `par`
+template <int N> struct DPack { double v[N]; };
+template <typename T>
+NNDT_DEVINL DPack<Vec<T>::N> network_sum(const Common<T>& c, int par, int chan, int i) {
+  constexpr int N = Vec<T>::N;
+  const size_t off = (size_t)(par * c.C + chan) * c.n_pad + i;
+  DPack<N> r;
+  if (c.sum_mc != nullptr) {
+#pragma unroll
+    for (int u = 0; u < N; ++u)
+      asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f64 %0, [%1];" : "=d"(r.v[u]) : "l"(c.sum_mc + off + u) : "memory");
+  } else {
+#pragma unroll
+    for (int u = 0; u < N; u += 2) {
+      const double2 q = *reinterpret_cast<const double2*>(c.sum_local + off + u);
+      r.v[u] = q.x; r.v[u + 1] = q.y;
+    }
+  }
+  return r;
+}
+// every rank's partial sum of round k must be in place before the in-switch reduction reads it
+template <typename T>
+NNDT_DEVINL void wait_all_sums(const Common<T>& c, int k) {
+  if (c.world > 1) {
+    if ((int)threadIdx.x < c.world && (int)threadIdx.x != c.rank) {
+      const long long t0 = clock64();
+      while (ld_acquire_sys(c.sum_flags + threadIdx.x) < k + 1) {
+        if (clock64() - t0 > kSpinLimit) { *c.err = 1; break; }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T>
+NNDT_DEVINL Pack<T> sum_partials(const Common<T>& c, int l, int i) {
+  // all (up to 16) partial loads are issued before the first add: one L2 round trip instead of S dependent ones;
+  // the summation order stays s = 0, 1, 2, ...
+  constexpr int N = Vec<T>::N, U = 16;
+  const T* gp = c.grad_part + (size_t)l * c.S * c.n_pad + i;
+  Pack<T> q[U];
+#pragma unroll
+  for (int s = 0; s < U; ++s)
+    if (s < c.S) q[s] = ldv(gp + (size_t)s * c.n_pad);
+  Pack<T> g = q[0];
+#pragma unroll
+  for (int s = 1; s < U; ++s)
+    if (s < c.S) {
+#pragma unroll
+      for (int u = 0; u < N; ++u) g.v[u] += q[s].v[u];
+    }
+  for (int s = U; s < c.S; ++s) {
+    const Pack<T> r = ldv(gp + (size_t)s * c.n_pad);
+#pragma unroll
+    for (int u = 0; u < N; ++u) g.v[u] += r.v[u];
+  }
+  return g;
+}
+
+// step bookkeeping done by one thread per node in the kernel that consumes a gradient: advance the sampler's
+// draw counter and fold the step's training loss into the moving average (problems/dist_online_dense_problem.py:129-137)
+template <typename T>
+NNDT_DEVINL void step_bookkeeping(const Common<T>& c, int l) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (c.calls != nullptr) c.calls[l] += 1;
+    if (c.tloss != nullptr) {
+      float loss = 0.f;
+      for (int s = 0; s < c.loss_S; ++s) loss += c.loss_part[l * c.loss_S + s];
+      const float t = c.tloss[l];
+      c.tloss[l] = t != 0.f ? (1.f - c.tdecay) * t + c.tdecay * loss : loss;
+    }
+  }
+}
+
+// ---- DiNNO arithmetic on one vector (optimizers/dinno.py:74-91): augmented-Lagrangian gradient + optimizer step ----
+template <typename T>
+struct DinnoCoef {
+  T rho, lr, step_size, bc2s;
+  int deg, opt;
+};
+template <typename T>
+NNDT_DEVINL DinnoCoef<T> dinno_coef(const DinnoArgs<T>& a, int k, int step, int deg) {
+  DinnoCoef<T> q;
+  q.rho = a.c.rho[k]; q.lr = a.c.lr[k];
+  const int t = a.persistent ? k * a.pits + step + 1 : step + 1;
+  const T bc1 = (T)1 - pow((T)0.9, (T)t);
+  q.bc2s = sqrt((T)1 - pow((T)0.999, (T)t));
+  q.step_size = q.lr / bc1;
+  q.deg = deg; q.opt = a.opt;
+  return q;
+}
+template <typename T>
+NNDT_DEVINL void dinno_apply(const DinnoCoef<T>& q, Pack<T>& th, const Pack<T>& thk, const Pack<T>& dl, const Pack<T>& du,
+                             Pack<T>& m, Pack<T>& v, const Pack<T>& gl) {
+  constexpr int N = Vec<T>::N;
+  const T b1 = (T)0.9, b2 = (T)0.999, eps = (T)1e-8, wd = (T)1e-2;
+  Pack<T> g;
+#pragma unroll
+  for (int u = 0; u < N; ++u)
+    g.v[u] = gl.v[u] + du.v[u] + (T)2 * q.rho * (T)q.deg * (th.v[u] - thk.v[u]) - q.rho * dl.v[u];
+  if (q.opt == kSGD) {
+#pragma unroll
+    for (int u = 0; u < N; ++u) th.v[u] -= q.lr * g.v[u];
+  } else {
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+      if (q.opt == kAdamW) th.v[u] *= ((T)1 - q.lr * wd);
+      m.v[u] = b1 * m.v[u] + ((T)1 - b1) * g.v[u];
+      v.v[u] = b2 * v.v[u] + ((T)1 - b2) * g.v[u] * g.v[u];
+      th.v[u] -= q.step_size * m.v[u] / (sqrt(v.v[u]) / q.bc2s + eps);
+    }
+  }
+}
+
+}  // namespace consensus
+}  // namespace nndt

@@ -1,0 +1,469 @@
+// Device-side building blocks of the MNIST conv-net forward/backward (shared by mnist.cu's per-step kernel
+// and dinno_round.cu's one-launch-per-round cluster kernel).
+#pragma once
+#include "common.cuh"
+#include "sampler.cuh"
+#include "mnist.h"
+
+namespace nndt {
+namespace mnist {
+
+constexpr int F = 3, KS = 5, HW = 28, PHW = 12, NPOOL = 144;
+constexpr int FC1_IN = 432, HID = 64, NCLS = 10;
+constexpr int W1_STRIDE = 436;          // padded fc1 row stride in smem (floats)
+constexpr int XROW = 22;                // padded row stride of the even/odd column planes
+constexpr int XPLANE = HW * XROW;       // 616 floats per plane
+constexpr int CGROUP = 256;             // threads cooperating on one conv channel in the backward
+
+// NT threads per CTA: 64 hidden units x (NT/64) k-slices must tile the 108 float4 of an fc1 row.
+template <int NT> struct Geo {
+  static constexpr int KSLICES = NT / 64;
+  static constexpr int K4S = (FC1_IN / 4) / KSLICES;
+  static_assert((FC1_IN / 4) % KSLICES == 0, "NT/64 must divide 108");
+  static_assert(NT >= 3 * CGROUP && NT >= FC1_IN, "need >= 768 threads");
+};
+
+template <int SPB, int NT>
+struct Smem {
+  float w1[HID * W1_STRIDE];            // fc1 weights; later scratch for dW1 transposition / conv-grad reduce
+  float xe[SPB * XPLANE];
+  float xo[SPB * XPLANE];
+  float a1[SPB * FC1_IN];
+  float da1[SPB * FC1_IN];
+  float hpart[Geo<NT>::KSLICES * SPB * HID];
+  float h[SPB * HID];
+  float dh[SPB * HID];
+  float dhT[HID * 8];                   // [j][s], row padded to 8 samples -> two 128-bit broadcast loads
+  float w2[NCLS * HID];
+  float z[SPB * 16];
+  float dz[SPB * 16];
+  float wc[F * KS * KS + 4];
+  float red[80];
+  float b1[HID];
+  float b2[16];
+  int sidx[SPB];
+  int label[SPB];
+  float valid[SPB];
+  unsigned char arg[SPB * FC1_IN];
+  alignas(8) uint64_t w1_bar;           // TMA transaction barrier of the fc1 weight staging
+};
+
+template <int SPB, int NT>
+__device__ __forceinline__ void load_images(Smem<SPB, NT>& sm, const Args& a, int tid) {
+  // 196 groups of 4 pixels per sample; issue every global load of this thread before the
+  // first conversion so the latencies overlap
+  constexpr int PER = (SPB * 196 + NT - 1) / NT;
+  uint32_t raw_u8[PER];
+  float4 raw_f[PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int o = tid + i * NT;
+    raw_u8[i] = 0; raw_f[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (o < SPB * 196) {
+      const int s = o / 196, q = o - s * 196;
+      if (sm.valid[s] != 0.f) {
+        const size_t base = (size_t)sm.sidx[s] * 784 + 4 * q;
+        if (a.x_is_u8) raw_u8[i] = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const unsigned char*>(a.x) + base);
+        else raw_f[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.x) + base);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int o = tid + i * NT;
+    if (o < SPB * 196) {
+      const int s = o / 196, q = o - s * 196;
+      const int row = (4 * q) / HW, col = (4 * q) - row * HW;
+      float v0, v1, v2, v3;
+      if (a.x_is_u8) {
+        const bool ok = sm.valid[s] != 0.f;
+        const uint32_t p = raw_u8[i];
+        v0 = ok ? ((p & 0xff) * (1.f / 255.f) - a.mean) * a.inv_std : 0.f;
+        v1 = ok ? (((p >> 8) & 0xff) * (1.f / 255.f) - a.mean) * a.inv_std : 0.f;
+        v2 = ok ? (((p >> 16) & 0xff) * (1.f / 255.f) - a.mean) * a.inv_std : 0.f;
+        v3 = ok ? ((p >> 24) * (1.f / 255.f) - a.mean) * a.inv_std : 0.f;
+      } else {
+        v0 = raw_f[i].x; v1 = raw_f[i].y; v2 = raw_f[i].z; v3 = raw_f[i].w;
+      }
+      float* e = sm.xe + s * XPLANE + row * XROW + (col >> 1);
+      float* d = sm.xo + s * XPLANE + row * XROW + (col >> 1);
+      e[0] = v0; d[0] = v1; e[1] = v2; d[1] = v3;
+    }
+  }
+}
+
+// pixel (r, c) of sample s
+template <int SPB, int NT>
+__device__ __forceinline__ float px(const Smem<SPB, NT>& sm, int s, int r, int c) {
+  return ((c & 1) ? sm.xo : sm.xe)[s * XPLANE + r * XROW + (c >> 1)];
+}
+
+template <int SPB, int NT>
+__device__ __forceinline__ void conv_relu_pool(Smem<SPB, NT>& sm, int tid) {
+  for (int it = tid; it < SPB * NPOOL; it += NT) {
+    const int s = it / NPOOL, p = it - s * NPOOL;
+    const int py = p / PHW, pxx = p - py * PHW;
+    float patch[6][6];
+    const float* e = sm.xe + s * XPLANE + (2 * py) * XROW + pxx;
+    const float* o = sm.xo + s * XPLANE + (2 * py) * XROW + pxx;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        patch[r][2 * c] = e[r * XROW + c];
+        patch[r][2 * c + 1] = o[r * XROW + c];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < F; ++c) {
+      float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll
+      for (int ky = 0; ky < KS; ++ky) {
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx) {
+          const float w = sm.wc[c * 25 + ky * 5 + kx];
+          acc[0][0] = fmaf(w, patch[ky][kx], acc[0][0]);
+          acc[0][1] = fmaf(w, patch[ky][kx + 1], acc[0][1]);
+          acc[1][0] = fmaf(w, patch[ky + 1][kx], acc[1][0]);
+          acc[1][1] = fmaf(w, patch[ky + 1][kx + 1], acc[1][1]);
+        }
+      }
+      // first maximum wins, like ATen's max_pool2d
+      float m = acc[0][0]; int ai = 0;
+      if (acc[0][1] > m) { m = acc[0][1]; ai = 1; }
+      if (acc[1][0] > m) { m = acc[1][0]; ai = 2; }
+      if (acc[1][1] > m) { m = acc[1][1]; ai = 3; }
+      m += sm.wc[75 + c];
+      sm.a1[s * FC1_IN + c * NPOOL + p] = fmaxf(m, 0.f);
+      sm.arg[s * FC1_IN + c * NPOOL + p] = (unsigned char)ai;
+    }
+  }
+}
+
+template <int SPB, int NT>
+__device__ __forceinline__ void fc1_forward(Smem<SPB, NT>& sm, int tid) {
+  constexpr int K4S = Geo<NT>::K4S;
+  const int j = tid & 63, ks = tid >> 6;
+  float acc[SPB];
+#pragma unroll
+  for (int s = 0; s < SPB; ++s) acc[s] = 0.f;
+  const float4* wrow = reinterpret_cast<const float4*>(sm.w1 + j * W1_STRIDE) + ks * K4S;
+  const float4* arow = reinterpret_cast<const float4*>(sm.a1) + ks * K4S;
+#pragma unroll
+  for (int i = 0; i < K4S; ++i) {
+    const float4 w = wrow[i];
+#pragma unroll
+    for (int s = 0; s < SPB; ++s) {
+      const float4 x = arow[s * (FC1_IN / 4) + i];
+      acc[s] = fmaf(w.x, x.x, fmaf(w.y, x.y, fmaf(w.z, x.z, fmaf(w.w, x.w, acc[s]))));
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < SPB; ++s) sm.hpart[(ks * SPB + s) * HID + j] = acc[s];
+}
+
+// stage fc1 weights with the TMA engine (one bulk copy per 1728-byte row into the padded smem rows,
+// completion tracked by an mbarrier transaction count) and the small tensors with L2 loads
+template <int SPB, int NT>
+__device__ __forceinline__ void stage_params(Smem<SPB, NT>& sm, const Args& a, const float* th, int tid, bool init_bar) {
+  // warp 1 drives the TMA engine (each lane queues two row copies) and warps 2+ fetch the small tensors, so
+  // warp 0 is free to run the sampler chain (draw counter -> permutation -> label) that gates the image loads
+  const float* w1g = th + a.off_w1;
+  if ((tid >> 5) == 1) {
+    const int lane = tid & 31;
+    if (lane == 0) {
+      if (init_bar) mbarrier_init(&sm.w1_bar, 1);
+      mbarrier_expect_tx(&sm.w1_bar, HID * FC1_IN * 4);
+    }
+    __syncwarp();
+    for (int j = lane; j < HID; j += 32) tma_bulk_g2s(sm.w1 + j * W1_STRIDE, w1g + j * FC1_IN, FC1_IN * 4, &sm.w1_bar);
+  }
+  if (tid >= 64) {
+    const int t2 = tid - 64;
+    if (t2 < 75) sm.wc[t2] = __ldcg(th + a.off_wc + t2);
+    else if (t2 < 78) sm.wc[t2] = __ldcg(th + a.off_bc + (t2 - 75));
+    else if (t2 >= 96 && t2 < 96 + HID) sm.b1[t2 - 96] = __ldcg(th + a.off_b1 + (t2 - 96));
+    else if (t2 >= 160 && t2 < 160 + NCLS) sm.b2[t2 - 160] = __ldcg(th + a.off_b2 + (t2 - 160));
+    for (int o = t2; o < NCLS * HID; o += NT - 64) sm.w2[o] = __ldcg(th + a.off_w2 + o);
+  }
+}
+
+// where the minibatch of draw `call` of node l lives
+struct BatchGeom { uint32_t bs, start, key, m; int shard_off; float inv_bs; };
+template <bool TRAIN>
+__device__ __forceinline__ BatchGeom batch_geom(const Args& a, int l, int call) {
+  BatchGeom g{0, 0, 0, 0, 0, 1.f};
+  if (TRAIN) {
+    if (a.direct) {
+      g.bs = a.direct_bs != nullptr ? (uint32_t)a.direct_bs[l] : (uint32_t)a.batch;
+    } else {
+      g.m = (uint32_t)a.shard_len[l];
+      g.shard_off = a.shard_off[l];
+      const BatchLoc loc = locate_batch((uint32_t)call, g.m, (uint32_t)a.batch);
+      g.bs = loc.size; g.start = loc.start;
+      g.key = mix_key((uint32_t)a.seed, (uint32_t)(a.node0 + l), loc.epoch);
+    }
+    g.inv_bs = 1.f / (float)(g.bs ? g.bs : 1);
+  }
+  return g;
+}
+
+// optional %globaltimer stamps of the phase boundaries (profiling builds of the round kernel only)
+__device__ __forceinline__ void phase_stamp(long long* prof, int idx, int tid) {
+  if (prof != nullptr && tid == 0) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    prof[idx] = t;
+  }
+}
+
+// One CTA's share of a step: SPB samples of node l (slice `slice` of S when training, chunk `chunk` of the
+// validation set otherwise).  Training writes the slice's partial gradient row and loss.
+template <int SPB, int NT, bool TRAIN>
+__device__ __forceinline__ void process_chunk(Smem<SPB, NT>& sm, const Args& a, int l, int slice, int S, int chunk,
+                                              const BatchGeom& bg, uint32_t w1_parity, int tid,
+                                              long long* prof = nullptr) {
+  constexpr int KSLICES = Geo<NT>::KSLICES, K4S = Geo<NT>::K4S;
+  const uint32_t bs = bg.bs, start = bg.start, key = bg.key, m = bg.m;
+  const int shard_off = bg.shard_off;
+  const float inv_bs = bg.inv_bs;
+    // ---- which samples ---------------------------------------------------------------------
+    int lab = 0;   // label load stays in flight across the barrier; it is only needed by the loss
+    if (tid < SPB) {
+      int idx = 0; float ok = 0.f;
+      if (TRAIN) {
+        const uint32_t t = slice * SPB + tid;
+        if (t < bs) {
+          ok = 1.f;
+          idx = a.direct ? (int)(l * a.batch + t) : shard_off + (int)feistel_permute(start + t, m, key);
+        }
+      } else {
+        const int t = chunk * SPB + tid;
+        if (t < a.n_val) { ok = 1.f; idx = t; }
+      }
+      sm.sidx[tid] = idx;
+      sm.valid[tid] = ok;
+      if (ok != 0.f) lab = (int)a.y[idx];
+    }
+    __syncthreads();
+    phase_stamp(prof, 0, tid);
+    load_images<SPB, NT>(sm, a, tid);
+    if (tid < SPB) sm.label[tid] = lab;
+    __syncthreads();
+    phase_stamp(prof, 1, tid);
+    conv_relu_pool<SPB, NT>(sm, tid);
+    mbarrier_wait_parity(&sm.w1_bar, w1_parity);   // fc1 weights have landed (no-op after the first chunk)
+    __syncthreads();
+    phase_stamp(prof, 2, tid);
+
+    // ---- fc1 -------------------------------------------------------------------------------
+    fc1_forward<SPB, NT>(sm, tid);
+    __syncthreads();
+    phase_stamp(prof, 3, tid);
+    for (int o = tid; o < SPB * HID; o += NT) {
+      const int s = o >> 6, j = o & 63;
+      float v = sm.b1[j];
+#pragma unroll
+      for (int ks = 0; ks < KSLICES; ++ks) v += sm.hpart[(ks * SPB + s) * HID + j];
+      sm.h[o] = fmaxf(v, 0.f);
+    }
+    __syncthreads();
+    phase_stamp(prof, 4, tid);
+
+    // ---- fc2 + log-softmax + NLL -----------------------------------------------------------
+    {
+      // 8 lanes per logit, each over 8 hidden units, then a 3-step shuffle tree (a single thread per logit
+      // would be a 64-deep dependent FMA chain)
+      const int o = tid >> 3, part = tid & 7;
+      const bool live = o < SPB * NCLS;
+      const int s = live ? o / NCLS : 0, c = live ? o - s * NCLS : 0;
+      float v = 0.f;
+      if (live) {
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const int j = part * 8 + jj;
+          v = fmaf(sm.h[s * HID + j], sm.w2[c * HID + j], v);
+        }
+      }
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      if (live && part == 0) sm.z[s * 16 + c] = v + sm.b2[c];
+    }
+    __syncthreads();
+    phase_stamp(prof, 5, tid);
+    if (tid < SPB) {
+      const int s = tid;
+      float mx = sm.z[s * 16];
+      int am = 0;
+#pragma unroll
+      for (int c = 1; c < NCLS; ++c) if (sm.z[s * 16 + c] > mx) { mx = sm.z[s * 16 + c]; am = c; }
+      float se = 0.f;
+#pragma unroll
+      for (int c = 0; c < NCLS; ++c) se += __expf(sm.z[s * 16 + c] - mx);
+      const float lse = mx + __logf(se);
+      const int y = sm.label[s];
+      const float ok = sm.valid[s];
+      const float loss = ok * (lse - sm.z[s * 16 + y]);
+      if (TRAIN) {
+#pragma unroll
+        for (int c = 0; c < NCLS; ++c)
+          sm.dz[s * 16 + c] = ok * inv_bs * (__expf(sm.z[s * 16 + c] - lse) - (c == y ? 1.f : 0.f));
+        sm.red[s] = loss;
+      } else if (ok != 0.f) {
+        const size_t o = (size_t)l * a.n_val + sm.sidx[s];
+        a.val_loss[o] = loss;
+        a.val_correct[o] = (unsigned char)(am == y);
+      }
+    }
+    __syncthreads();
+    phase_stamp(prof, 6, tid);
+    if (!TRAIN) return;
+
+    float* gp = a.grad_part + ((size_t)l * S + slice) * a.n_pad;
+    if (tid == 0) {
+      float tot = 0.f;
+#pragma unroll
+      for (int s = 0; s < SPB; ++s) tot += sm.red[s];
+      a.loss_part[l * S + slice] = tot * inv_bs;
+    }
+    // ---- fc2 grads, dh ----------------------------------------------------------------------
+    for (int o = tid; o < NCLS * HID; o += NT) {
+      const int c = o >> 6, j = o & 63;
+      float v = 0.f;
+#pragma unroll
+      for (int s = 0; s < SPB; ++s) v = fmaf(sm.dz[s * 16 + c], sm.h[s * HID + j], v);
+      gp[a.off_w2 + o] = v;
+    }
+    if (tid < NCLS) {
+      float v = 0.f;
+#pragma unroll
+      for (int s = 0; s < SPB; ++s) v += sm.dz[s * 16 + tid];
+      gp[a.off_b2 + tid] = v;
+    }
+    for (int o = tid; o < SPB * HID; o += NT) {
+      const int s = o >> 6, j = o & 63;
+      float v = 0.f;
+#pragma unroll
+      for (int c = 0; c < NCLS; ++c) v = fmaf(sm.dz[s * 16 + c], sm.w2[c * HID + j], v);
+      v = sm.h[o] > 0.f ? v : 0.f;
+      sm.dh[o] = v;
+      sm.dhT[j * 8 + s] = v;
+    }
+    __syncthreads();
+    phase_stamp(prof, 7, tid);
+    if (tid < HID) {
+      float v = 0.f;
+#pragma unroll
+      for (int s = 0; s < SPB; ++s) v += sm.dh[s * HID + tid];
+      gp[a.off_b1 + tid] = v;
+    }
+    // ---- da1 = dh . W1 (masked by ReLU): one fc1 input k per thread ---------------------------
+    if (tid < FC1_IN) {
+      float acc[SPB];
+#pragma unroll
+      for (int s = 0; s < SPB; ++s) acc[s] = 0.f;
+#pragma unroll 8
+      for (int j = 0; j < HID; ++j) {
+        const float w = sm.w1[j * W1_STRIDE + tid];
+        const float4 d0 = *reinterpret_cast<const float4*>(sm.dhT + j * 8);
+        float4 d1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (SPB > 4) d1 = *reinterpret_cast<const float4*>(sm.dhT + j * 8 + 4);
+        const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+        for (int s = 0; s < SPB; ++s) acc[s] = fmaf(dv[s], w, acc[s]);
+      }
+#pragma unroll
+      for (int s = 0; s < SPB; ++s) {
+        const int k = s * FC1_IN + tid;
+        sm.da1[k] = sm.a1[k] > 0.f ? acc[s] : 0.f;
+      }
+    }
+    // ---- dW1[j][k] = sum_s dh[s][j] a1[s][k]: register tile per (j, k-slice) -------------------
+    float4 dw[K4S];
+    {
+      const int j = tid & 63, ks = tid >> 6;
+#pragma unroll
+      for (int i = 0; i < K4S; ++i) dw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4* arow = reinterpret_cast<const float4*>(sm.a1) + ks * K4S;
+#pragma unroll
+      for (int s = 0; s < SPB; ++s) {
+        const float d = sm.dh[s * HID + j];
+#pragma unroll
+        for (int i = 0; i < K4S; ++i) {
+          const float4 x = arow[s * (FC1_IN / 4) + i];
+          dw[i].x = fmaf(d, x.x, dw[i].x);
+          dw[i].y = fmaf(d, x.y, dw[i].y);
+          dw[i].z = fmaf(d, x.z, dw[i].z);
+          dw[i].w = fmaf(d, x.w, dw[i].w);
+        }
+      }
+    }
+    __syncthreads();   // every read of the staged W1 is done: its smem becomes scratch
+    phase_stamp(prof, 8, tid);
+    {
+      // transpose through smem so the global stores are fully coalesced
+      const int j = tid & 63, ks = tid >> 6;
+      float4* srow = reinterpret_cast<float4*>(sm.w1 + j * W1_STRIDE) + ks * K4S;
+#pragma unroll
+      for (int i = 0; i < K4S; ++i) srow[i] = dw[i];
+    }
+    __syncthreads();
+    phase_stamp(prof, 9, tid);
+    {
+      float4* out = reinterpret_cast<float4*>(gp + a.off_w1);
+      for (int o = tid; o < HID * (FC1_IN / 4); o += NT) {
+        const int j = o / (FC1_IN / 4), k4 = o - j * (FC1_IN / 4);
+        out[o] = *reinterpret_cast<const float4*>(sm.w1 + j * W1_STRIDE + 4 * k4);
+      }
+    }
+    // ---- conv grads: each pooled cell routes da1 to its argmax conv position ------------------
+    // 3 groups of 256 threads, one per channel; partial sums are transposed through smem
+    // (scratch = the dead W1 region) and reduced by warps — no 26x5 shuffle trees.
+    float cacc[26];
+#pragma unroll
+    for (int i = 0; i < 26; ++i) cacc[i] = 0.f;
+    const int cg = tid / CGROUP, ct = tid - cg * CGROUP;
+    if (cg < F) {
+      for (int it = ct; it < SPB * NPOOL; it += CGROUP) {
+        const int s = it / NPOOL, p = it - s * NPOOL;
+        const float g = sm.da1[s * FC1_IN + cg * NPOOL + p];
+        if (g != 0.f) {
+          const int ai = sm.arg[s * FC1_IN + cg * NPOOL + p];
+          const int py = p / PHW, pxx = p - py * PHW;
+          const int r0 = 2 * py + (ai >> 1), c0 = 2 * pxx + (ai & 1);
+#pragma unroll
+          for (int ky = 0; ky < KS; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < KS; ++kx)
+              cacc[ky * 5 + kx] = fmaf(g, px<SPB, NT>(sm, s, r0 + ky, c0 + kx), cacc[ky * 5 + kx]);
+          cacc[25] += g;
+        }
+      }
+    }
+    __syncthreads();   // dW1 copy-out finished reading the scratch
+    phase_stamp(prof, 10, tid);
+    float* scratch = sm.w1;   // [78][CGROUP]
+    if (cg < F) {
+#pragma unroll
+      for (int i = 0; i < 26; ++i) scratch[(cg * 26 + i) * CGROUP + ct] = cacc[i];
+    }
+    __syncthreads();
+    phase_stamp(prof, 11, tid);
+    {
+      const int warp = tid >> 5, lane = tid & 31;
+      for (int o = warp; o < 78; o += NT / 32) {
+        float v = 0.f;
+#pragma unroll
+        for (int q = 0; q < CGROUP / 32; ++q) v += scratch[o * CGROUP + lane + 32 * q];
+        v = warp_sum(v);
+        if (lane == 0) {
+          const int c = o / 26, i = o - c * 26;
+          gp[(i < 25) ? a.off_wc + c * 25 + i : a.off_bc + c] = v;
+        }
+      }
+    }
+}
+
+}  // namespace mnist
+}  // namespace nndt

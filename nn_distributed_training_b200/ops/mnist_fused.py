@@ -6,12 +6,24 @@ stateless sampler, the per-slice gradient partials and the validation outputs.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
 from . import load_ext
 
-SPB = 8  # samples per CTA (template instantiation in mnist.cu)
+SPB = 8  # samples per CTA of the evaluation kernel / upper bound for training (template instantiations in mnist.cu)
+
+
+def choose_spb(batch: int, n_local: int, sms: int) -> int:
+    """Samples per training CTA (4..8).  A node's batch is cut into ceil(batch/spb) CTAs; per-CTA time grows
+    with spb (conv / fc work) on top of a fixed part (weight staging, dW1 write-out), so the best choice is
+    the smallest spb whose L x S CTAs still fit in ONE wave of the SMs (1 CTA/SM: ~200 KB smem, 768 threads)."""
+    for spb in range(4, SPB + 1):
+        if n_local * -(-batch // spb) <= sms:
+            return spb
+    return SPB
 
 
 class FusedMnist:
@@ -22,7 +34,11 @@ class FusedMnist:
         a, pl = problem.arena, problem.placement
         self.L, self.n_pad = pl.L, a.n_pad
         self.B = problem.train_batch_size
-        self.S = -(-self.B // SPB)
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        self.spb = (int(os.environ.get("NNDT_SPB", "0")) or int(problem.conf.get("samples_per_cta", 0))
+                    or choose_spb(self.B, self.L, sms))
+        assert 4 <= self.spb <= SPB
+        self.S = -(-self.B // self.spb)
         sh = problem.shards
         self.x = sh.x.reshape(sh.x.shape[0], -1).contiguous()
         assert self.x.shape[1] == 784
@@ -48,7 +64,7 @@ class FusedMnist:
             shard_off=self.shard_off.data_ptr(), shard_len=self.shard_len.data_ptr(),
             calls=self.calls.data_ptr(),
             grad_part=self.grad_part.data_ptr(), loss_part=self.loss_part.data_ptr(),
-            spb=SPB, S=self.S)
+            spb=self.spb, S=self.S)
         self.train_op = self.ext.MnistOp(self.base)
         self._setup_eval()
         self.host_feed = None
@@ -58,6 +74,30 @@ class FusedMnist:
         """Enqueue fwd+bwd of the next batch of every local node (graph-capturable).
         The draw counter is advanced by the consensus kernel that consumes the partials."""
         self.train_op.train()
+
+    # ---- one launch per DiNNO round (csrc/dinno_round.cu) -----------------------
+    MAX_ROUND_STEPS = 8
+
+    def supports_round_kernel(self, opt) -> bool:
+        """The cluster kernel needs the node's S batch slices in one cluster (S <= 8 CTAs) and fp32 state."""
+        return (opt.alg_name == "dinno" and self.spb == SPB and self.S <= 8 and 1 <= opt.pits <= self.MAX_ROUND_STEPS
+                and self.pr.arena.dtype == torch.float32 and self.ext.dinno_round_max_clusters(self.S) >= 1)
+
+    def round_op(self, cons_dict, stage_set=None):
+        """``DinnoRoundOp`` running all primal iterations of a round; ``stage_set`` selects the host-fed
+        staging buffers (one batch source per step) instead of the resident shards."""
+        P = int(cons_dict["pits"])
+        md = dict(self.base)
+        if getattr(self, "round_prof", None) is not None:
+            md["prof"] = self.round_prof.data_ptr()     # scripts/profile_round_phases.py
+        if stage_set is None:
+            steps = [dict(x=self.x.data_ptr(), y=self.y.data_ptr(), direct_bs=None) for _ in range(P)]
+        else:
+            md.update(direct=1)
+            b = stage_set
+            steps = [dict(x=self.x_stage[b, p].data_ptr(), y=self.y_stage[b, p].data_ptr(),
+                          direct_bs=self.bs_stage[b, p].data_ptr()) for p in range(P)]
+        return self.ext.DinnoRoundOp(md, cons_dict, steps)
 
     def compute_grads(self) -> torch.Tensor:
         """Eager API: fills ``arena.grad`` and advances the counters itself."""

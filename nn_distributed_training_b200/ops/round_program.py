@@ -2,6 +2,8 @@
 
 A round is a short, fixed kernel sequence
     DiNNO:  [fwd/bwd, dinno_update(p)] x primal_iterations
+            (MNIST: ONE cluster kernel per round, csrc/dinno_round.cu — fwd/bwd and the update of
+             every primal iteration separated by cluster barriers instead of kernel boundaries)
     DSGD :  dsgd_mix, fwd/bwd, dsgd_step
     DSGT :  dsgt_mix, fwd/bwd, dsgt_track
 whose per-round scalars come from device schedules indexed by a device round
@@ -28,16 +30,18 @@ def _nvtx(name):
     return torch.cuda.nvtx.range(name)
 
 
-def _round_ops(opt, eng, grads):
+def _round_ops(opt, eng, grads, round_op=None):
     with _nvtx(f"consensus_round/{opt.alg_name}"):
-        _round_ops_impl(opt, eng, grads)
+        _round_ops_impl(opt, eng, grads, round_op)
 
 
-def _round_ops_impl(opt, eng, grads):
+def _round_ops_impl(opt, eng, grads, round_op=None):
     alg = opt.alg_name
     if eng.sum_mode:
         eng.op.local_sum()   # complete graph: per-rank partial sums feeding the NVLS reduction
-    if alg == "dinno":
+    if round_op is not None:
+        round_op.launch()    # whole DiNNO round (all primal iterations) in one cluster launch
+    elif alg == "dinno":
         for p in range(opt.pits):
             grads(p)
             eng.op.dinno_update(p)
@@ -74,6 +78,7 @@ class RoundProgram:
         self.capturable = pr.fused is not None and os.environ.get("NNDT_NO_GRAPH", "0") != "1"
         self._graphs: Dict[int, torch.cuda.CUDAGraph] = {}
         self.host_mode = False
+        self._round_ops = None
         if pr.fused is not None:
             pr.fused.sync_calls_from_host()
             if pr.conf.get("input_pipeline", "resident") == "host":
@@ -85,6 +90,25 @@ class RoundProgram:
                 self.host_mode = True
                 self._runner = None
                 self._stage_set = 0
+            # opt-in: measured slower than the PDL-overlapped per-step kernels (docs/perf_notes.md), kept as the
+            # in-kernel phase profiler (scripts/profile_round_phases.py) and for launch-bound environments
+            want = pr.conf.get("fused_round", opt.conf.get("fused_round", False)) or os.environ.get("NNDT_FUSED_ROUND") == "1"
+            if (want and os.environ.get("NNDT_NO_FUSED_ROUND", "0") != "1"
+                    and getattr(pr.fused, "supports_round_kernel", lambda o: False)(opt)):
+                sets = [0, 1] if self.host_mode else [None]
+                self._round_ops = {b: pr.fused.round_op(self.eng._keep, b) for b in sets}
+
+    def round_op(self):
+        if self._round_ops is None:
+            return None
+        return self._round_ops[self._stage_set if self.host_mode else None]
+
+    def launches_per_round(self) -> int:
+        """Kernel launches of one communication round (excluding the host-feed staging kernel)."""
+        n = 1 if self.eng.sum_mode else 0
+        if self._round_ops is not None:
+            return n + 1
+        return n + (2 * self.opt.pits if self.opt.alg_name == "dinno" else 3)
 
     def grads(self, p: int = 0):
         pr = self.pr
@@ -117,7 +141,7 @@ class RoundProgram:
                 self._stage_set = b
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    _round_ops(self.opt, self.eng, self.grads)
+                    _round_ops(self.opt, self.eng, self.grads, self.round_op())
                     fz.loss_readback()
                 graphs.append(g)
             if fz.host_feed["mode"] == "gpu_pull":
@@ -141,12 +165,12 @@ class RoundProgram:
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):
                         for _ in range(r):
-                            _round_ops(self.opt, self.eng, self.grads)
+                            _round_ops(self.opt, self.eng, self.grads, self.round_op())
                     self._graphs[r] = g
                 g.replay()
             else:
                 for _ in range(r):
-                    _round_ops(self.opt, self.eng, self.grads)
+                    _round_ops(self.opt, self.eng, self.grads, self.round_op())
             self._count(r)
             left -= r
 
