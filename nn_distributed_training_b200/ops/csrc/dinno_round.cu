@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(NT, 1) dinno_round_kernel(const RoundArgs ra) 
   const size_t row = (size_t)l * c.n_pad;
   float* th_row = c.theta + row;
   const float* thk_row = pub_row(c, ri.par, 0, l);
-  const int calls0 = c.calls != nullptr ? c.calls[l] : 0;
+  const int calls0 = ra.m.calls != nullptr ? ra.m.calls[l] : 0;
   const int nvec = c.n_pad >> 2, per = (nvec + S - 1) / S;
   const int v0 = slice * per, v1 = min(nvec, v0 + per);
   const int pits = ra.d.pits;
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(NT, 1) dinno_round_kernel(const RoundArgs ra) 
       stamp(prof, cta, 5 + 4 * p, tid);
     }
   }
-  if (slice == 0 && tid == 0 && c.calls != nullptr) c.calls[l] = calls0 + pits;
+  if (slice == 0 && tid == 0 && ra.m.calls != nullptr) ra.m.calls[l] = calls0 + pits;
   finish_round(c, ri.k);
   stamp(prof, cta, 63, tid);
 }

@@ -21,7 +21,9 @@ struct Args {
   const int* direct_bs;   // [L] valid rows per node when direct (nullptr: all `batch`)
   const int* shard_off;   // [L]
   const int* shard_len;   // [L]
-  const int* calls;       // [L] draw counter per node (device, advanced by the update kernel)
+  int* calls;             // [L] draw counter per node (device); the training kernel advances it itself
+  unsigned int* arrive;   // [L] CTA arrival counters used to advance `calls` exactly once per launch
+  int tune;               // bit 0: sampler chain + row gather issued before the PDL wait
   // training outputs
   float* grad_part;       // [L, S, n_pad]
   float* loss_part;       // [L, S]

@@ -48,26 +48,34 @@ struct Smem {
   alignas(8) uint64_t w1_bar;           // TMA transaction barrier of the fc1 weight staging
 };
 
+// Pixel gather in two halves so other work can sit between the global loads and their first use:
+// 196 groups of 4 pixels per sample; every global load of a thread is issued before the first conversion.
 template <int SPB, int NT>
-__device__ __forceinline__ void load_images(Smem<SPB, NT>& sm, const Args& a, int tid) {
-  // 196 groups of 4 pixels per sample; issue every global load of this thread before the
-  // first conversion so the latencies overlap
-  constexpr int PER = (SPB * 196 + NT - 1) / NT;
-  uint32_t raw_u8[PER];
-  float4 raw_f[PER];
+struct ImgRegs {
+  static constexpr int PER = (SPB * 196 + NT - 1) / NT;
+  uint32_t u8[PER];
+  float4 f[PER];
+};
+template <int SPB, int NT>
+__device__ __forceinline__ void issue_image_loads(const Smem<SPB, NT>& sm, const Args& a, int tid, ImgRegs<SPB, NT>& r) {
+  constexpr int PER = ImgRegs<SPB, NT>::PER;
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
     const int o = tid + i * NT;
-    raw_u8[i] = 0; raw_f[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    r.u8[i] = 0; r.f[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (o < SPB * 196) {
       const int s = o / 196, q = o - s * 196;
       if (sm.valid[s] != 0.f) {
         const size_t base = (size_t)sm.sidx[s] * 784 + 4 * q;
-        if (a.x_is_u8) raw_u8[i] = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const unsigned char*>(a.x) + base);
-        else raw_f[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.x) + base);
+        if (a.x_is_u8) r.u8[i] = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const unsigned char*>(a.x) + base);
+        else r.f[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.x) + base);
       }
     }
   }
+}
+template <int SPB, int NT>
+__device__ __forceinline__ void commit_images(Smem<SPB, NT>& sm, const Args& a, int tid, const ImgRegs<SPB, NT>& r) {
+  constexpr int PER = ImgRegs<SPB, NT>::PER;
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
     const int o = tid + i * NT;
@@ -77,13 +85,13 @@ __device__ __forceinline__ void load_images(Smem<SPB, NT>& sm, const Args& a, in
       float v0, v1, v2, v3;
       if (a.x_is_u8) {
         const bool ok = sm.valid[s] != 0.f;
-        const uint32_t p = raw_u8[i];
+        const uint32_t p = r.u8[i];
         v0 = ok ? ((p & 0xff) * (1.f / 255.f) - a.mean) * a.inv_std : 0.f;
         v1 = ok ? (((p >> 8) & 0xff) * (1.f / 255.f) - a.mean) * a.inv_std : 0.f;
         v2 = ok ? (((p >> 16) & 0xff) * (1.f / 255.f) - a.mean) * a.inv_std : 0.f;
         v3 = ok ? ((p >> 24) * (1.f / 255.f) - a.mean) * a.inv_std : 0.f;
       } else {
-        v0 = raw_f[i].x; v1 = raw_f[i].y; v2 = raw_f[i].z; v3 = raw_f[i].w;
+        v0 = r.f[i].x; v1 = r.f[i].y; v2 = r.f[i].z; v3 = r.f[i].w;
       }
       float* e = sm.xe + s * XPLANE + row * XROW + (col >> 1);
       float* d = sm.xo + s * XPLANE + row * XROW + (col >> 1);
@@ -217,39 +225,52 @@ __device__ __forceinline__ void phase_stamp(long long* prof, int idx, int tid) {
   }
 }
 
-// One CTA's share of a step: SPB samples of node l (slice `slice` of S when training, chunk `chunk` of the
-// validation set otherwise).  Training writes the slice's partial gradient row and loss.
+// ---- data half of a step: which samples, then their pixels into the even/odd smem planes --------------------
+// Reads only the dataset and the sampler state, never parameters.  `select_samples` returns the label (load in
+// flight) for threads < SPB; the caller stores it with `commit_labels` once the images are committed.
 template <int SPB, int NT, bool TRAIN>
-__device__ __forceinline__ void process_chunk(Smem<SPB, NT>& sm, const Args& a, int l, int slice, int S, int chunk,
+__device__ __forceinline__ int select_samples(Smem<SPB, NT>& sm, const Args& a, int l, int slice, int chunk,
+                                              const BatchGeom& bg, int tid) {
+  int lab = 0;   // label load stays in flight across the barrier; it is only needed by the loss
+  if (tid < SPB) {
+    int idx = 0; float ok = 0.f;
+    if (TRAIN) {
+      const uint32_t t = slice * SPB + tid;
+      if (t < bg.bs) {
+        ok = 1.f;
+        idx = a.direct ? (int)(l * a.batch + t) : bg.shard_off + (int)feistel_permute(bg.start + t, bg.m, bg.key);
+      }
+    } else {
+      const int t = chunk * SPB + tid;
+      if (t < a.n_val) { ok = 1.f; idx = t; }
+    }
+    sm.sidx[tid] = idx;
+    sm.valid[tid] = ok;
+    if (ok != 0.f) lab = (int)a.y[idx];
+  }
+  __syncthreads();
+  return lab;
+}
+template <int SPB, int NT, bool TRAIN>
+__device__ __forceinline__ void load_chunk(Smem<SPB, NT>& sm, const Args& a, int l, int slice, int chunk,
+                                           const BatchGeom& bg, int tid, long long* prof = nullptr) {
+  const int lab = select_samples<SPB, NT, TRAIN>(sm, a, l, slice, chunk, bg, tid);
+  phase_stamp(prof, 0, tid);
+  ImgRegs<SPB, NT> r;
+  issue_image_loads<SPB, NT>(sm, a, tid, r);
+  commit_images<SPB, NT>(sm, a, tid, r);
+  if (tid < SPB) sm.label[tid] = lab;
+}
+
+// ---- compute half: forward, loss, backward of the SPB samples staged by load_chunk -----------------------------
+// Training writes the slice's partial gradient row and loss.
+template <int SPB, int NT, bool TRAIN>
+__device__ __forceinline__ void compute_chunk(Smem<SPB, NT>& sm, const Args& a, int l, int slice, int S,
                                               const BatchGeom& bg, uint32_t w1_parity, int tid,
                                               long long* prof = nullptr) {
   constexpr int KSLICES = Geo<NT>::KSLICES, K4S = Geo<NT>::K4S;
-  const uint32_t bs = bg.bs, start = bg.start, key = bg.key, m = bg.m;
-  const int shard_off = bg.shard_off;
   const float inv_bs = bg.inv_bs;
-    // ---- which samples ---------------------------------------------------------------------
-    int lab = 0;   // label load stays in flight across the barrier; it is only needed by the loss
-    if (tid < SPB) {
-      int idx = 0; float ok = 0.f;
-      if (TRAIN) {
-        const uint32_t t = slice * SPB + tid;
-        if (t < bs) {
-          ok = 1.f;
-          idx = a.direct ? (int)(l * a.batch + t) : shard_off + (int)feistel_permute(start + t, m, key);
-        }
-      } else {
-        const int t = chunk * SPB + tid;
-        if (t < a.n_val) { ok = 1.f; idx = t; }
-      }
-      sm.sidx[tid] = idx;
-      sm.valid[tid] = ok;
-      if (ok != 0.f) lab = (int)a.y[idx];
-    }
-    __syncthreads();
-    phase_stamp(prof, 0, tid);
-    load_images<SPB, NT>(sm, a, tid);
-    if (tid < SPB) sm.label[tid] = lab;
-    __syncthreads();
+    __syncthreads();   // images + staged small tensors visible
     phase_stamp(prof, 1, tid);
     conv_relu_pool<SPB, NT>(sm, tid);
     mbarrier_wait_parity(&sm.w1_bar, w1_parity);   // fc1 weights have landed (no-op after the first chunk)
@@ -465,5 +486,17 @@ __device__ __forceinline__ void process_chunk(Smem<SPB, NT>& sm, const Args& a, 
     }
 }
 
+}  // namespace mnist
+}  // namespace nndt
+
+namespace nndt {
+namespace mnist {
+template <int SPB, int NT, bool TRAIN>
+__device__ __forceinline__ void process_chunk(Smem<SPB, NT>& sm, const Args& a, int l, int slice, int S, int chunk,
+                                              const BatchGeom& bg, uint32_t w1_parity, int tid,
+                                              long long* prof = nullptr) {
+  load_chunk<SPB, NT, TRAIN>(sm, a, l, slice, chunk, bg, tid, prof);
+  compute_chunk<SPB, NT, TRAIN>(sm, a, l, slice, S, bg, w1_parity, tid, prof);
+}
 }  // namespace mnist
 }  // namespace nndt

@@ -130,6 +130,8 @@ class ConsensusEngine:
         # ---- gradient source --------------------------------------------------------
         if pr.fused is not None:
             grad_part, S, calls = pr.fused.grad_part, pr.fused.S, pr.fused.calls
+            if getattr(pr.fused, "owns_calls", False):
+                calls = None       # the forward/backward kernel advances its own draw counters
         else:
             grad_part, S, calls = a.grad, 1, None
         self.S = S

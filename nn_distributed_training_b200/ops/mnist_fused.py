@@ -50,6 +50,8 @@ class FusedMnist:
         self.shard_off = torch.tensor(sh.offsets[:-1], dtype=torch.int32, device=dev)
         self.shard_len = torch.tensor(sh.sizes, dtype=torch.int32, device=dev)
         self.calls = torch.zeros(self.L, dtype=torch.int32, device=dev)
+        self.arrive = torch.zeros(self.L, dtype=torch.int32, device=dev)
+        self.owns_calls = True      # the training kernel advances the draw counters (not the consensus kernels)
         self.grad_part = torch.zeros(self.L, self.S, self.n_pad, dtype=torch.float32, device=dev)
         self.loss_part = torch.zeros(self.L, self.S, dtype=torch.float32, device=dev)
         off = {s.name: s.offset for s in a.layout.slots}
@@ -62,9 +64,9 @@ class FusedMnist:
             mean=float(mean), inv_std=1.0 / float(std),
             direct=0, batch=self.B, seed=problem.seed, node0=pl.lo,
             shard_off=self.shard_off.data_ptr(), shard_len=self.shard_len.data_ptr(),
-            calls=self.calls.data_ptr(),
+            calls=self.calls.data_ptr(), arrive=self.arrive.data_ptr(),
             grad_part=self.grad_part.data_ptr(), loss_part=self.loss_part.data_ptr(),
-            spb=self.spb, S=self.S)
+            spb=self.spb, S=self.S, tune=int(os.environ.get("NNDT_MNIST_TUNE", "1")))
         self.train_op = self.ext.MnistOp(self.base)
         self._setup_eval()
         self.host_feed = None
@@ -104,7 +106,6 @@ class FusedMnist:
         pr = self.pr
         self.launch()
         torch.sum(self.grad_part, dim=1, out=pr.arena.grad)
-        self.calls += 1
         pr.count_draws_all(1)
         pr.last_losses = self.loss_part.sum(1)
         return pr.last_losses
