@@ -37,7 +37,7 @@ struct MnistOp {
     a.x_is_u8 = geti(d, "x_is_u8"); a.mean = (float)getf(d, "mean"); a.inv_std = (float)getf(d, "inv_std", 1.0);
     a.direct = geti(d, "direct"); a.batch = geti(d, "batch"); a.seed = geti(d, "seed"); a.node0 = geti(d, "node0");
     a.shard_off = ptr<const int>(d, "shard_off"); a.shard_len = ptr<const int>(d, "shard_len");
-    a.calls = ptr<int>(d, "calls"); a.arrive = ptr<unsigned int>(d, "arrive"); a.tune = geti(d, "tune", 1); a.direct_bs = ptr<const int>(d, "direct_bs");
+    a.calls = ptr<int>(d, "calls"); a.arrive = ptr<unsigned int>(d, "arrive"); a.tune = geti(d, "tune", 1); a.prof = ptr<long long>(d, "step_prof"); a.direct_bs = ptr<const int>(d, "direct_bs");
     a.grad_part = ptr<float>(d, "grad_part"); a.loss_part = ptr<float>(d, "loss_part");
     a.n_val = geti(d, "n_val"); a.val_loss = ptr<float>(d, "val_loss");
     a.val_correct = ptr<unsigned char>(d, "val_correct");

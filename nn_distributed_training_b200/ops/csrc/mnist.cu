@@ -34,6 +34,8 @@ __global__ void __launch_bounds__(NT, 1) mnist_kernel(const Args a) {
     // tune bit 0 the sampler chain and the HBM row gather are issued BEFORE the programmatic-dependency wait,
     // while the consensus kernel is still producing the parameters; the pixels are converted after the wait,
     // under the shadow of the parameter staging.
+    long long* prof = a.prof != nullptr ? a.prof + (l * gridDim.x + blockIdx.x) * 64 : nullptr;
+    phase_stamp(prof, 20, tid);
     const bool early = (a.tune & 1) != 0;
     if (!early) {
       pdl_wait();
@@ -43,6 +45,7 @@ __global__ void __launch_bounds__(NT, 1) mnist_kernel(const Args a) {
     const int call = a.calls != nullptr ? a.calls[l] : 0;
     const BatchGeom bg = batch_geom<true>(a, l, call);
     const int lab = select_samples<SPB, NT, true>(sm, a, l, blockIdx.x, 0, bg, tid);
+    phase_stamp(prof, 21, tid);
     ImgRegs<SPB, NT> img;
     issue_image_loads<SPB, NT>(sm, a, tid, img);
     if (tid == 0 && a.calls != nullptr && a.arrive != nullptr) {
@@ -52,11 +55,13 @@ __global__ void __launch_bounds__(NT, 1) mnist_kernel(const Args a) {
     if (early) {
       pdl_wait();               // parameters of this step are now final
       pdl_launch_dependents();
+      phase_stamp(prof, 22, tid);
       stage_params<SPB, NT>(sm, a, th, tid, true);
     }
     commit_images<SPB, NT>(sm, a, tid, img);
     if (tid < SPB) sm.label[tid] = lab;
-    compute_chunk<SPB, NT, true>(sm, a, l, blockIdx.x, gridDim.x, bg, 0, tid);
+    compute_chunk<SPB, NT, true>(sm, a, l, blockIdx.x, gridDim.x, bg, 0, tid, prof);
+    phase_stamp(prof, 23, tid);
   } else {
     pdl_wait();
     pdl_launch_dependents();

@@ -10,7 +10,9 @@ namespace mnist {
 
 constexpr int F = 3, KS = 5, HW = 28, PHW = 12, NPOOL = 144;
 constexpr int FC1_IN = 432, HID = 64, NCLS = 10;
-constexpr int W1_STRIDE = 436;          // padded fc1 row stride in smem (floats)
+constexpr int W1_STRIDE = 436;          // padded fc1 row stride in smem (floats): conflict-free mma fragment loads
+constexpr int A1_STRIDE = 436;          // same padding for the fc1 input rows (B / A fragments of the three GEMMs)
+constexpr int KGROUPS = 6;              // fc1: the 54 k-steps of 8 are split over 6 warp groups
 constexpr int XROW = 22;                // padded row stride of the even/odd column planes
 constexpr int XPLANE = HW * XROW;       // 616 floats per plane
 constexpr int CGROUP = 256;             // threads cooperating on one conv channel in the backward
@@ -28,9 +30,9 @@ struct Smem {
   float w1[HID * W1_STRIDE];            // fc1 weights; later scratch for dW1 transposition / conv-grad reduce
   float xe[SPB * XPLANE];
   float xo[SPB * XPLANE];
-  float a1[SPB * FC1_IN];
+  float a1[8 * A1_STRIDE];              // fc1 input [sample][k]; rows >= SPB stay zero (K / N padding of the MMAs)
   float da1[SPB * FC1_IN];
-  float hpart[Geo<NT>::KSLICES * SPB * HID];
+  float hpart[KGROUPS * 8 * HID];       // fc1 partial sums [k-group][sample][j]
   float h[SPB * HID];
   float dh[SPB * HID];
   float dhT[HID * 8];                   // [j][s], row padded to 8 samples -> two 128-bit broadcast loads
@@ -142,32 +144,73 @@ __device__ __forceinline__ void conv_relu_pool(Smem<SPB, NT>& sm, int tid) {
       if (acc[1][0] > m) { m = acc[1][0]; ai = 2; }
       if (acc[1][1] > m) { m = acc[1][1]; ai = 3; }
       m += sm.wc[75 + c];
-      sm.a1[s * FC1_IN + c * NPOOL + p] = fmaxf(m, 0.f);
+      sm.a1[s * A1_STRIDE + c * NPOOL + p] = fmaxf(m, 0.f);
       sm.arg[s * FC1_IN + c * NPOOL + p] = (unsigned char)ai;
     }
   }
 }
 
+// ---- tensor-core helpers for the three fc1-sized GEMMs (64 x 432 x <=8 samples) -----------------------------
+// mma.sync m16n8k8 TF32 with the 3xTF32 split (x = hi + lo, both TF32; a.b ~ a_lo.b_hi + a_hi.b_lo + a_hi.b_hi),
+// which keeps fp32-level accuracy: the framework's contract is fp32 training, not TF32.  A tcgen05 tile does not
+// fit here: the split needs hi and lo copies of the 110 KB weight tile in shared memory, and a 64 x 8 output
+// tile would use <1% of a UMMA anyway — these GEMMs are latency-, not throughput-bound.
+// Fragment coordinates (g = lane >> 2, t = lane & 3):
+//   A (16x8, row major): a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4)
+//   B (8x8, col major) : b0 (k=t, n=g) b1 (k=t+4, n=g)
+//   C (16x8)           : c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+struct FragA { uint32_t hi[4], lo[4]; };
+struct FragB { uint32_t hi[2], lo[2]; };
+__device__ __forceinline__ FragA make_frag_a(float a0, float a1, float a2, float a3) {
+  FragA f;
+  split_tf32(a0, f.hi[0], f.lo[0]); split_tf32(a1, f.hi[1], f.lo[1]);
+  split_tf32(a2, f.hi[2], f.lo[2]); split_tf32(a3, f.hi[3], f.lo[3]);
+  return f;
+}
+__device__ __forceinline__ FragB make_frag_b(float b0, float b1) {
+  FragB f;
+  split_tf32(b0, f.hi[0], f.lo[0]); split_tf32(b1, f.hi[1], f.lo[1]);
+  return f;
+}
+__device__ __forceinline__ void mma3(float (&c)[4], const FragA& a, const FragB& b) {
+  mma_tf32(c, a.lo, b.hi);   // small terms first
+  mma_tf32(c, a.hi, b.lo);
+  mma_tf32(c, a.hi, b.hi);
+}
+
+// fc1 pre-activation partials: hpart[kg][s][j] = sum_{k in group kg} W1[j][k] a1[s][k]
+// warp w: rows j0 = 16 (w & 3), k-group kg = w >> 2 (9 k-steps of 8)
 template <int SPB, int NT>
 __device__ __forceinline__ void fc1_forward(Smem<SPB, NT>& sm, int tid) {
-  constexpr int K4S = Geo<NT>::K4S;
-  const int j = tid & 63, ks = tid >> 6;
-  float acc[SPB];
-#pragma unroll
-  for (int s = 0; s < SPB; ++s) acc[s] = 0.f;
-  const float4* wrow = reinterpret_cast<const float4*>(sm.w1 + j * W1_STRIDE) + ks * K4S;
-  const float4* arow = reinterpret_cast<const float4*>(sm.a1) + ks * K4S;
-#pragma unroll
-  for (int i = 0; i < K4S; ++i) {
-    const float4 w = wrow[i];
-#pragma unroll
-    for (int s = 0; s < SPB; ++s) {
-      const float4 x = arow[s * (FC1_IN / 4) + i];
-      acc[s] = fmaf(w.x, x.x, fmaf(w.y, x.y, fmaf(w.z, x.z, fmaf(w.w, x.w, acc[s]))));
-    }
+  static_assert(NT == 768, "24 warps = 4 row tiles x 6 k-groups");
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int j0 = 16 * (warp & 3), kg = warp >> 2;
+  float c[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* wa = sm.w1 + (j0 + g) * W1_STRIDE + t;
+  const float* xb = sm.a1 + g * A1_STRIDE + t;
+#pragma unroll 3
+  for (int i = 0; i < 9; ++i) {
+    const int k0 = (kg * 9 + i) * 8;
+    const FragA a = make_frag_a(wa[k0], wa[8 * W1_STRIDE + k0], wa[k0 + 4], wa[8 * W1_STRIDE + k0 + 4]);
+    const FragB b = make_frag_b(xb[k0], xb[k0 + 4]);
+    mma3(c, a, b);
   }
-#pragma unroll
-  for (int s = 0; s < SPB; ++s) sm.hpart[(ks * SPB + s) * HID + j] = acc[s];
+  float* hp = sm.hpart + (kg * 8) * HID;
+  hp[(2 * t) * HID + j0 + g] = c[0];
+  hp[(2 * t + 1) * HID + j0 + g] = c[1];
+  hp[(2 * t) * HID + j0 + g + 8] = c[2];
+  hp[(2 * t + 1) * HID + j0 + g + 8] = c[3];
 }
 
 // stage fc1 weights with the TMA engine (one bulk copy per 1728-byte row into the padded smem rows,
@@ -197,10 +240,10 @@ __device__ __forceinline__ void stage_params(Smem<SPB, NT>& sm, const Args& a, c
 }
 
 // where the minibatch of draw `call` of node l lives
-struct BatchGeom { uint32_t bs, start, key, m; int shard_off; float inv_bs; };
+struct BatchGeom { uint32_t bs, start, key, m; int shard_off; float inv_bs; int call; };
 template <bool TRAIN>
 __device__ __forceinline__ BatchGeom batch_geom(const Args& a, int l, int call) {
-  BatchGeom g{0, 0, 0, 0, 0, 1.f};
+  BatchGeom g{0, 0, 0, 0, 0, 1.f, call};
   if (TRAIN) {
     if (a.direct) {
       g.bs = a.direct_bs != nullptr ? (uint32_t)a.direct_bs[l] : (uint32_t)a.batch;
@@ -268,8 +311,11 @@ template <int SPB, int NT, bool TRAIN>
 __device__ __forceinline__ void compute_chunk(Smem<SPB, NT>& sm, const Args& a, int l, int slice, int S,
                                               const BatchGeom& bg, uint32_t w1_parity, int tid,
                                               long long* prof = nullptr) {
-  constexpr int KSLICES = Geo<NT>::KSLICES, K4S = Geo<NT>::K4S;
   const float inv_bs = bg.inv_bs;
+    if (SPB < 8) {   // sample padding of the MMA operands (never written afterwards)
+      for (int o = tid; o < (8 - SPB) * A1_STRIDE; o += NT) sm.a1[SPB * A1_STRIDE + o] = 0.f;
+      for (int o = tid; o < HID * 8; o += NT) if ((o & 7) >= SPB) sm.dhT[o] = 0.f;
+    }
     __syncthreads();   // images + staged small tensors visible
     phase_stamp(prof, 1, tid);
     conv_relu_pool<SPB, NT>(sm, tid);
@@ -285,7 +331,7 @@ __device__ __forceinline__ void compute_chunk(Smem<SPB, NT>& sm, const Args& a, 
       const int s = o >> 6, j = o & 63;
       float v = sm.b1[j];
 #pragma unroll
-      for (int ks = 0; ks < KSLICES; ++ks) v += sm.hpart[(ks * SPB + s) * HID + j];
+      for (int kg = 0; kg < KGROUPS; ++kg) v += sm.hpart[(kg * 8 + s) * HID + j];
       sm.h[o] = fmaxf(v, 0.f);
     }
     __syncthreads();
@@ -313,6 +359,21 @@ __device__ __forceinline__ void compute_chunk(Smem<SPB, NT>& sm, const Args& a, 
     }
     __syncthreads();
     phase_stamp(prof, 5, tid);
+    if (TRAIN && (a.tune & 2) && !a.direct && tid >= 64 && tid < 64 + SPB * 8) {
+      // warps 2+ idle through the 8-thread softmax: pull the rows of this slice's NEXT draw into L2
+      const int s = (tid - 64) >> 3, line = (tid - 64) & 7;        // 784 B (u8) = 7 x 128 B lines per row
+      const BatchLoc loc = locate_batch((uint32_t)(bg.call + 1), bg.m, (uint32_t)a.batch);
+      const uint32_t t = slice * SPB + s;
+      if (t < loc.size) {
+        const uint32_t key = mix_key((uint32_t)a.seed, (uint32_t)(a.node0 + l), loc.epoch);
+        const size_t idx = (size_t)bg.shard_off + feistel_permute(loc.start + t, bg.m, key);
+        const size_t row_bytes = a.x_is_u8 ? 784 : 784 * 4;
+        const char* row = reinterpret_cast<const char*>(a.x) + idx * row_bytes;
+        for (size_t o = (size_t)line * 128; o < row_bytes; o += 1024)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
+        if (line == 7) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.y + idx));
+      }
+    }
     if (tid < SPB) {
       const int s = tid;
       float mx = sm.z[s * 16];
@@ -379,65 +440,53 @@ __device__ __forceinline__ void compute_chunk(Smem<SPB, NT>& sm, const Args& a, 
       for (int s = 0; s < SPB; ++s) v += sm.dh[s * HID + tid];
       gp[a.off_b1 + tid] = v;
     }
-    // ---- da1 = dh . W1 (masked by ReLU): one fc1 input k per thread ---------------------------
-    if (tid < FC1_IN) {
-      float acc[SPB];
-#pragma unroll
-      for (int s = 0; s < SPB; ++s) acc[s] = 0.f;
-#pragma unroll 8
-      for (int j = 0; j < HID; ++j) {
-        const float w = sm.w1[j * W1_STRIDE + tid];
-        const float4 d0 = *reinterpret_cast<const float4*>(sm.dhT + j * 8);
-        float4 d1 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (SPB > 4) d1 = *reinterpret_cast<const float4*>(sm.dhT + j * 8 + 4);
-        const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-#pragma unroll
-        for (int s = 0; s < SPB; ++s) acc[s] = fmaf(dv[s], w, acc[s]);
-      }
-#pragma unroll
-      for (int s = 0; s < SPB; ++s) {
-        const int k = s * FC1_IN + tid;
-        sm.da1[k] = sm.a1[k] > 0.f ? acc[s] : 0.f;
-      }
-    }
-    // ---- dW1[j][k] = sum_s dh[s][j] a1[s][k]: register tile per (j, k-slice) -------------------
-    float4 dw[K4S];
     {
-      const int j = tid & 63, ks = tid >> 6;
-#pragma unroll
-      for (int i = 0; i < K4S; ++i) dw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4* arow = reinterpret_cast<const float4*>(sm.a1) + ks * K4S;
-#pragma unroll
-      for (int s = 0; s < SPB; ++s) {
-        const float d = sm.dh[s * HID + j];
-#pragma unroll
-        for (int i = 0; i < K4S; ++i) {
-          const float4 x = arow[s * (FC1_IN / 4) + i];
-          dw[i].x = fmaf(d, x.x, dw[i].x);
-          dw[i].y = fmaf(d, x.y, dw[i].y);
-          dw[i].z = fmaf(d, x.z, dw[i].z);
-          dw[i].w = fmaf(d, x.w, dw[i].w);
+      const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+      // ---- da1[s][k] = relu'(a1) * sum_j dh[s][j] W1[j][k]: out tile [16 k][8 s], A = W1^T, B = dh^T ---------
+      for (int mt = warp; mt < FC1_IN / 16; mt += NT / 32) {
+        const int k0 = 16 * mt;
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        const float* wa = sm.w1 + t * W1_STRIDE + k0 + g;
+        const float* db = sm.dhT + t * 8 + g;
+#pragma unroll 4
+        for (int js = 0; js < HID / 8; ++js) {
+          const int j0 = 8 * js;
+          const FragA af = make_frag_a(wa[j0 * W1_STRIDE], wa[j0 * W1_STRIDE + 8], wa[(j0 + 4) * W1_STRIDE],
+                                       wa[(j0 + 4) * W1_STRIDE + 8]);
+          const FragB bf = make_frag_b(db[j0 * 8], db[(j0 + 4) * 8]);
+          mma3(c, af, bf);
+        }
+        const int s0 = 2 * t, ka = k0 + g, kb = k0 + g + 8;
+        if (s0 < SPB) {
+          sm.da1[s0 * FC1_IN + ka] = sm.a1[s0 * A1_STRIDE + ka] > 0.f ? c[0] : 0.f;
+          sm.da1[s0 * FC1_IN + kb] = sm.a1[s0 * A1_STRIDE + kb] > 0.f ? c[2] : 0.f;
+        }
+        if (s0 + 1 < SPB) {
+          sm.da1[(s0 + 1) * FC1_IN + ka] = sm.a1[(s0 + 1) * A1_STRIDE + ka] > 0.f ? c[1] : 0.f;
+          sm.da1[(s0 + 1) * FC1_IN + kb] = sm.a1[(s0 + 1) * A1_STRIDE + kb] > 0.f ? c[3] : 0.f;
+        }
+      }
+      // ---- dW1[j][k] = sum_s dh[s][j] a1[s][k]: one k-step (8 samples); warp = 16 rows x 9 column tiles; the C
+      //      fragments go straight to global memory (every store instruction fills eight whole 32-byte sectors)
+      {
+        const int j0 = 16 * (warp & 3), ng = warp >> 2;
+        const float* da = sm.dhT + (j0 + g) * 8 + t;
+        const FragA af = make_frag_a(da[0], da[64], da[4], da[68]);
+        const float* xb = sm.a1 + t * A1_STRIDE + g;
+        float* out = gp + a.off_w1 + (j0 + g) * FC1_IN + 2 * t;
+#pragma unroll 3
+        for (int i = 0; i < 9; ++i) {
+          const int k0 = (ng * 9 + i) * 8;
+          const FragB bf = make_frag_b(xb[k0], xb[4 * A1_STRIDE + k0]);
+          float c[4] = {0.f, 0.f, 0.f, 0.f};
+          mma3(c, af, bf);
+          *reinterpret_cast<float2*>(out + k0) = make_float2(c[0], c[1]);
+          *reinterpret_cast<float2*>(out + 8 * FC1_IN + k0) = make_float2(c[2], c[3]);
         }
       }
     }
-    __syncthreads();   // every read of the staged W1 is done: its smem becomes scratch
+    __syncthreads();   // da1 complete; every read of the staged W1 is done: its smem becomes scratch
     phase_stamp(prof, 8, tid);
-    {
-      // transpose through smem so the global stores are fully coalesced
-      const int j = tid & 63, ks = tid >> 6;
-      float4* srow = reinterpret_cast<float4*>(sm.w1 + j * W1_STRIDE) + ks * K4S;
-#pragma unroll
-      for (int i = 0; i < K4S; ++i) srow[i] = dw[i];
-    }
-    __syncthreads();
-    phase_stamp(prof, 9, tid);
-    {
-      float4* out = reinterpret_cast<float4*>(gp + a.off_w1);
-      for (int o = tid; o < HID * (FC1_IN / 4); o += NT) {
-        const int j = o / (FC1_IN / 4), k4 = o - j * (FC1_IN / 4);
-        out[o] = *reinterpret_cast<const float4*>(sm.w1 + j * W1_STRIDE + 4 * k4);
-      }
-    }
     // ---- conv grads: each pooled cell routes da1 to its argmax conv position ------------------
     // 3 groups of 256 threads, one per channel; partial sums are transposed through smem
     // (scratch = the dead W1 region) and reduced by warps — no 26x5 shuffle trees.
@@ -452,25 +501,27 @@ __device__ __forceinline__ void compute_chunk(Smem<SPB, NT>& sm, const Args& a, 
         if (g != 0.f) {
           const int ai = sm.arg[s * FC1_IN + cg * NPOOL + p];
           const int py = p / PHW, pxx = p - py * PHW;
-          const int r0 = 2 * py + (ai >> 1), c0 = 2 * pxx + (ai & 1);
+          // window origin (2 py + ai/2, 2 pxx + ai%2): column parity decides which plane serves the even / odd
+          // taps, so two base pointers turn every tap into one immediate-offset LDS
+          const int par = ai & 1, base = s * XPLANE + (2 * py + (ai >> 1)) * XROW + pxx;
+          const float* pA = (par ? sm.xo : sm.xe) + base;        // taps kx = 0, 2, 4
+          const float* pB = (par ? sm.xe + 1 : sm.xo) + base;    // taps kx = 1, 3
 #pragma unroll
           for (int ky = 0; ky < KS; ++ky)
 #pragma unroll
             for (int kx = 0; kx < KS; ++kx)
-              cacc[ky * 5 + kx] = fmaf(g, px<SPB, NT>(sm, s, r0 + ky, c0 + kx), cacc[ky * 5 + kx]);
+              cacc[ky * 5 + kx] = fmaf(g, ((kx & 1) ? pB : pA)[ky * XROW + (kx >> 1)], cacc[ky * 5 + kx]);
           cacc[25] += g;
         }
       }
     }
-    __syncthreads();   // dW1 copy-out finished reading the scratch
-    phase_stamp(prof, 10, tid);
     float* scratch = sm.w1;   // [78][CGROUP]
     if (cg < F) {
 #pragma unroll
       for (int i = 0; i < 26; ++i) scratch[(cg * 26 + i) * CGROUP + ct] = cacc[i];
     }
     __syncthreads();
-    phase_stamp(prof, 11, tid);
+    phase_stamp(prof, 9, tid);
     {
       const int warp = tid >> 5, lane = tid & 31;
       for (int o = warp; o < 78; o += NT / 32) {

@@ -67,6 +67,9 @@ class FusedMnist:
             calls=self.calls.data_ptr(), arrive=self.arrive.data_ptr(),
             grad_part=self.grad_part.data_ptr(), loss_part=self.loss_part.data_ptr(),
             spb=self.spb, S=self.S, tune=int(os.environ.get("NNDT_MNIST_TUNE", "1")))
+        if os.environ.get("NNDT_STEP_PROF") == "1":     # scripts/profile_round_phases.py --per-step
+            self.step_prof = torch.zeros(self.L * self.S, 64, dtype=torch.int64, device=dev)
+            self.base["step_prof"] = self.step_prof.data_ptr()
         self.train_op = self.ext.MnistOp(self.base)
         self._setup_eval()
         self.host_feed = None
