@@ -188,7 +188,7 @@ def run_ours(args):
     assert ctx.world_size == args.gpus, f"launched with WORLD_SIZE={ctx.world_size} but --gpus {args.gpus}"
     n_nodes = NODES_PER_GPU * args.gpus
     W, K = args.warmup, args.steps
-    oits = max(PAPER_ROUNDS, 2 * (W + K) + 64)
+    oits = max(PAPER_ROUNDS, 4 * (W + K) + 64)
     dev = ctx.device
 
     def maxreduce(x):
@@ -233,7 +233,9 @@ def run_ours(args):
         W2 = max(W, 6)
         pr2 = build_problem(ctx, n_nodes, opt_conf(oits), eval_every=10 ** 9, extra={"input_pipeline": "host"})
         opt2 = DiNNO(pr2, dev, pr2.conf["optimizer_config"])
-        opt2.run_rounds(W2)                      # warm-up: captures both round graphs, fills the loader ring
+        opt2.run_rounds(W2)                      # warm-up: captures the round graphs, stages the first batch
+        for _ in range(2 if K % 2 else 1):       # untimed pass with the timed call's chunking (and staging parity),
+            opt2.run_rounds(K)                   # so no graph is captured inside the timed region
         torch.cuda.synchronize()
         ctx.barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -253,6 +255,8 @@ def run_ours(args):
                "h2d_bytes_per_step": int(hf["h2d_bytes"]), "d2h_bytes_per_step": int(hf["d2h_bytes"]),
                "api": "DiNNO(problem, device, conf).run_rounds(K) with problem conf input_pipeline=host",
                "h2d": hf["mode"] + ": every round's uint8 rows + labels are pulled from the pinned host dataset over PCIe",
+               "d2h": ("the training kernel stores every step's per-CTA losses into a pinned host buffer (device-initiated PCIe write)"
+                       if getattr(pr2.fused, "loss_mode", "") == "mirror" else "cudaMemcpyAsync D2H node per round"),
                "wall_ms_per_step": maxreduce(wall * 1e3) / K, "last_round_losses_read_back": last_losses[:3]}
         del opt2, pr2
     except Exception as e:  # noqa: BLE001

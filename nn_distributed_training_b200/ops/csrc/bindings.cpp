@@ -38,7 +38,7 @@ struct MnistOp {
     a.direct = geti(d, "direct"); a.batch = geti(d, "batch"); a.seed = geti(d, "seed"); a.node0 = geti(d, "node0");
     a.shard_off = ptr<const int>(d, "shard_off"); a.shard_len = ptr<const int>(d, "shard_len");
     a.calls = ptr<int>(d, "calls"); a.arrive = ptr<unsigned int>(d, "arrive"); a.tune = geti(d, "tune", 1); a.prof = ptr<long long>(d, "step_prof"); a.direct_bs = ptr<const int>(d, "direct_bs");
-    a.grad_part = ptr<float>(d, "grad_part"); a.loss_part = ptr<float>(d, "loss_part");
+    a.grad_part = ptr<float>(d, "grad_part"); a.loss_part = ptr<float>(d, "loss_part"); a.loss_mirror = ptr<float>(d, "loss_mirror");
     a.n_val = geti(d, "n_val"); a.val_loss = ptr<float>(d, "val_loss");
     a.val_correct = ptr<unsigned char>(d, "val_correct");
     spb = geti(d, "spb", 8); S = geti(d, "S", 1); eval_ctas = geti(d, "eval_ctas", 1);
@@ -56,7 +56,7 @@ struct GatherOp {
     a.P = geti(d, "P"); a.L = geti(d, "L"); a.batch = geti(d, "batch"); a.seed = geti(d, "seed"); a.node0 = geti(d, "node0");
     a.shard_off = ptr<const int>(d, "shard_off"); a.shard_len = ptr<const int>(d, "shard_len");
     a.calls0 = ptr<const int>(d, "calls0"); a.stage_round = ptr<int>(d, "stage_round");
-    a.done_ctr = ptr<unsigned int>(d, "done_ctr");
+    a.done_ctr = ptr<unsigned int>(d, "done_ctr"); a.max_blocks = geti(d, "max_blocks", 24);
   }
   void launch() { check(mnist::launch_gather(a, cur_stream()), "gather_rows"); }
 };

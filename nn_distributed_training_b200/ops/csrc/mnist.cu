@@ -98,31 +98,44 @@ static cudaError_t launch_t(const Args& a, int S, bool train, int eval_ctas, cud
 }
 
 // ---- device-initiated H2D staging of one round's minibatches (one warp per row) -------------------------
-__global__ void __launch_bounds__(256) gather_rows_kernel(const GatherArgs a) {
-  // few, long-lived blocks: the staging copy must leave most SMs (and their register files) to the
-  // training kernels it overlaps with; each warp streams several rows with all loads of a row in flight
+constexpr int kGatherThreads = 512;
+__global__ void __launch_bounds__(kGatherThreads) gather_rows_kernel(const GatherArgs a) {
+  // few, long-lived blocks: the staging copy must leave the SMs (and their register files) to the training CTAs
+  // it overlaps with.  PCIe reads have microseconds of latency, so each warp keeps TWO rows (1.5 KB) in flight.
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int rows = a.P * a.L * a.batch;
   const int r = *a.stage_round;
   const int n16 = a.row_bytes >> 4;
-  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += nwarps) {
-    const int t = row % a.batch, l = (row / a.batch) % a.L, p = row / (a.batch * a.L);
-    const uint32_t m = (uint32_t)a.shard_len[l];
-    const BatchLoc loc = locate_batch((uint32_t)(a.calls0[l] + r * a.P + p), m, (uint32_t)a.batch);
-    if (t == 0 && lane == 0) a.bs_stage[p * a.L + l] = (int)loc.size;
-    if ((uint32_t)t < loc.size) {
+  const int w0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  for (int row0 = w0; row0 < rows; row0 += 2 * nwarps) {
+    const uint4* s4[2] = {nullptr, nullptr};
+    uint4* d4[2] = {nullptr, nullptr};
+    uint4 v[2][2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int row = row0 + u * nwarps;
+      v[u][0] = v[u][1] = make_uint4(0, 0, 0, 0);
+      if (row >= rows) continue;
+      const int t = row % a.batch, l = (row / a.batch) % a.L, p = row / (a.batch * a.L);
+      const uint32_t m = (uint32_t)a.shard_len[l];
+      const BatchLoc loc = locate_batch((uint32_t)(a.calls0[l] + r * a.P + p), m, (uint32_t)a.batch);
+      if (t == 0 && lane == 0) a.bs_stage[p * a.L + l] = (int)loc.size;
+      if ((uint32_t)t >= loc.size) continue;
       const uint32_t key = mix_key((uint32_t)a.seed, (uint32_t)(a.node0 + l), loc.epoch);
       const size_t src = (size_t)a.shard_off[l] + feistel_permute(loc.start + t, m, key);
-      const uint4* s4 = reinterpret_cast<const uint4*>(a.x_host + src * a.row_bytes);
-      uint4* d4 = reinterpret_cast<uint4*>(a.x_stage + (size_t)row * a.row_bytes);
-      uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
-      if (lane < n16) v0 = s4[lane];
-      if (lane + 32 < n16) v1 = s4[lane + 32];
-      if (lane < n16) d4[lane] = v0;
-      if (lane + 32 < n16) d4[lane + 32] = v1;
-      for (int i = lane + 64; i < n16; i += 32) d4[i] = s4[i];
+      s4[u] = reinterpret_cast<const uint4*>(a.x_host + src * a.row_bytes);
+      d4[u] = reinterpret_cast<uint4*>(a.x_stage + (size_t)row * a.row_bytes);
+      if (lane < n16) v[u][0] = s4[u][lane];
+      if (lane + 32 < n16) v[u][1] = s4[u][lane + 32];
       if (lane == 0) a.y_stage[row] = a.y_host[src];
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (d4[u] == nullptr) continue;
+      if (lane < n16) d4[u][lane] = v[u][0];
+      if (lane + 32 < n16) d4[u][lane + 32] = v[u][1];
+      for (int i = lane + 64; i < n16; i += 32) d4[u][i] = s4[u][i];
     }
   }
   // last block advances the staged-round counter
@@ -135,9 +148,10 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const GatherArgs a) {
 }
 cudaError_t launch_gather(const GatherArgs& a, cudaStream_t st) {
   const int rows = a.P * a.L * a.batch;
-  int blocks = (rows * 32 + 255) / 256;
-  if (blocks > 24) blocks = 24;
-  gather_rows_kernel<<<blocks, 256, 0, st>>>(a);
+  int blocks = (rows * 32 + kGatherThreads - 1) / kGatherThreads;
+  const int cap = a.max_blocks > 0 ? a.max_blocks : 24;
+  if (blocks > cap) blocks = cap;
+  gather_rows_kernel<<<blocks, kGatherThreads, 0, st>>>(a);
   return cudaGetLastError();
 }
 

@@ -28,6 +28,7 @@ struct Args {
   // training outputs
   float* grad_part;       // [L, S, n_pad]
   float* loss_part;       // [L, S]
+  float* loss_mirror;     // [L, S] optional second destination in pinned host memory (device-initiated D2H of the result)
   // evaluation
   int n_val;
   float* val_loss;              // [L, n_val]
@@ -49,6 +50,7 @@ struct GatherArgs {
   const int* calls0;             // [L] draw counters at round 0 of the stream
   int* stage_round;              // [1] device counter of staged rounds (advanced by this kernel)
   unsigned int* done_ctr;        // [1]
+  int max_blocks;                // grid cap: the staging blocks must leave one SM per concurrent training CTA
 };
 cudaError_t launch_gather(const GatherArgs& a, cudaStream_t st);
 cudaError_t launch_train(const Args& a, int spb, int S, cudaStream_t st);

@@ -408,6 +408,7 @@ __device__ __forceinline__ void compute_chunk(Smem<SPB, NT>& sm, const Args& a, 
 #pragma unroll
       for (int s = 0; s < SPB; ++s) tot += sm.red[s];
       a.loss_part[l * S + slice] = tot * inv_bs;
+      if (a.loss_mirror != nullptr) a.loss_mirror[l * S + slice] = tot * inv_bs;   // zero-copy store to pinned host memory
     }
     // ---- fc2 grads, dh ----------------------------------------------------------------------
     for (int o = tid; o < NCLS * HID; o += NT) {

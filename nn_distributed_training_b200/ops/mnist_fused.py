@@ -99,6 +99,8 @@ class FusedMnist:
             steps = [dict(x=self.x.data_ptr(), y=self.y.data_ptr(), direct_bs=None) for _ in range(P)]
         else:
             md.update(direct=1)
+            if getattr(self, "loss_mode", "memcpy") == "mirror":
+                md.update(loss_mirror=self.loss_host.data_ptr())
             b = stage_set
             steps = [dict(x=self.x_stage[b, p].data_ptr(), y=self.y_stage[b, p].data_ptr(),
                           direct_bs=self.bs_stage[b, p].data_ptr()) for p in range(P)]
@@ -177,10 +179,18 @@ class FusedMnist:
         self.y_stage = torch.zeros(2, P, L, B, dtype=torch.int64, device=dev)
         self.bs_stage = torch.zeros(2, P, L, dtype=torch.int32, device=dev)
         self.loss_host = torch.zeros(L, self.S, dtype=torch.float32, pin_memory=True)
+        # result read-back: "mirror" = the training kernel stores each step's losses straight into this pinned host
+        # buffer over PCIe (no copy node on the round's critical path); "memcpy" = a D2H copy node per round
+        self.loss_mode = str(pr.conf.get("host_loss", os.environ.get("NNDT_HOST_LOSS", "mirror")))
         pl = pr.placement
         self.calls0 = torch.as_tensor(pr.calls[pl.lo: pl.lo + pl.L].astype(np.int32), device=dev)
         self.stage_round = torch.zeros(1, dtype=torch.int32, device=dev)
         self.stage_done = torch.zeros(1, dtype=torch.int32, device=dev)
+        # a training CTA fills an SM's register file (768 threads x 80 registers): a staging block that lands on
+        # an SM evicts a training CTA into a second wave, so the staging grid is sized to the SMs left over
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        free = sms - (self.L * self.S) % sms if (self.L * self.S) % sms else 0
+        gather_blocks = int(os.environ.get("NNDT_GATHER_BLOCKS", "0")) or max(4, min(24, free - 2))
         self.direct_ops, self.gather_ops = [], []
         for b in range(2):
             ops = []
@@ -188,6 +198,8 @@ class FusedMnist:
                 d = dict(self.base)
                 d.update(direct=1, x=self.x_stage[b, p].data_ptr(), y=self.y_stage[b, p].data_ptr(),
                          direct_bs=self.bs_stage[b, p].data_ptr())
+                if self.loss_mode == "mirror":
+                    d.update(loss_mirror=self.loss_host.data_ptr())
                 ops.append(self.ext.MnistOp(d))
             self.direct_ops.append(ops)
             self.gather_ops.append(self.ext.GatherOp(dict(
@@ -196,7 +208,7 @@ class FusedMnist:
                 bs_stage=self.bs_stage[b].data_ptr(), P=P, L=L, batch=B, seed=pr.seed, node0=pl.lo,
                 shard_off=self.shard_off.data_ptr(), shard_len=self.shard_len.data_ptr(),
                 calls0=self.calls0.data_ptr(), stage_round=self.stage_round.data_ptr(),
-                done_ctr=self.stage_done.data_ptr())))
+                done_ctr=self.stage_done.data_ptr(), max_blocks=gather_blocks)))
         self.loader = None
         self.host_feed = dict(P=P, nslots=2, mode="gpu_pull",
                               h2d_bytes=P * L * B * (784 * xb + 8), d2h_bytes=L * self.S * 4)
@@ -231,8 +243,10 @@ class FusedMnist:
         return self.runner
 
     def loss_readback(self):
-        """Enqueue the D2H read of the round's per-node losses."""
-        self.loss_host.copy_(self.loss_part, non_blocking=True)
+        """Enqueue the D2H read of the round's per-node losses (nothing to enqueue when the kernel mirrors them
+        into the pinned host buffer itself)."""
+        if getattr(self, "loss_mode", "memcpy") != "mirror":
+            self.loss_host.copy_(self.loss_part, non_blocking=True)
 
     # ---- validation ---------------------------------------------------------
     def _setup_eval(self):

@@ -23,6 +23,7 @@ import torch
 from .engine import ConsensusEngine
 
 MAX_ROUNDS_PER_GRAPH = 64
+PULL_ROUNDS_PER_GRAPH = 16     # host-fed (gpu_pull) rounds captured per graph, staging overlapped inside the graph
 
 
 def _nvtx(name):
@@ -90,6 +91,10 @@ class RoundProgram:
                 self.host_mode = True
                 self._runner = None
                 self._stage_set = 0
+                self._pull_graphs: Dict = {}
+                self._pull_parity = 0
+                self._pull_primed = False
+                self._side = None
             # opt-in: measured slower than the PDL-overlapped per-step kernels (docs/perf_notes.md), kept as the
             # in-kernel phase profiler (scripts/profile_round_phases.py) and for launch-bound environments
             want = pr.conf.get("fused_round", opt.conf.get("fused_round", False)) or os.environ.get("NNDT_FUSED_ROUND") == "1"
@@ -130,11 +135,55 @@ class RoundProgram:
         if self.pr.fused is not None:
             self.pr.count_draws_all(1)
 
-    def _run_host_fed(self, rounds: int):
-        """Host-fed rounds: the native runner issues, per round, the H2D copy of that round's
-        inputs (copy stream), the captured round graph (kernels + D2H loss read) and the slot
-        hand-back to the loader threads — Python only counts."""
+    def _capture_pull_graph(self, R: int, parity: int):
+        """``R`` host-fed rounds as ONE graph with two branches: while round i computes on the capture stream,
+        the staging kernel pulls round i+1's rows out of pinned host memory on a forked stream (device-initiated
+        H2D over PCIe); every round ends with the D2H read of its losses.  No CPU work per round at all."""
         fz = self.pr.fused
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.pr.device)
+        side = self._side
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            main = torch.cuda.current_stream(self.pr.device)
+            for i in range(R):
+                b = (parity + i) & 1
+                # set b^1 was last read by round i-1, which precedes this point on `main`
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    fz.gather_ops[b ^ 1].launch()
+                self._stage_set = b
+                _round_ops(self.opt, self.eng, self.grads, self.round_op())
+                fz.loss_readback()
+                main.wait_stream(side)     # round i+1 consumes what was just staged (also joins the fork)
+        return g
+
+    def _run_pull_graphs(self, rounds: int):
+        fz = self.pr.fused
+        if not self._pull_primed:
+            fz.gather_ops[self._pull_parity].launch()      # stage the very first round
+            self._pull_primed = True
+        left = rounds
+        while left > 0:
+            r = min(left, PULL_ROUNDS_PER_GRAPH)
+            key = (r, self._pull_parity)
+            g = self._pull_graphs.get(key)
+            if g is None:
+                g = self._pull_graphs[key] = self._capture_pull_graph(r, self._pull_parity)
+            g.replay()
+            self._pull_parity = (self._pull_parity + r) & 1
+            self._count(r)
+            left -= r
+
+    def _run_host_fed(self, rounds: int):
+        """Host-fed rounds.  ``gpu_pull`` (default): multi-round graphs with the staging kernel forked inside
+        (``_capture_pull_graph``); ``host_pull_driver: runner`` keeps the native two-stream driver
+        (csrc/runtime.cpp: PullRunner) that launches one staging graph + one round graph per round.
+        ``cpu_loader``: the native runner issues, per round, the H2D copy of that round's inputs, the captured
+        round graph (kernels + D2H loss read) and the slot hand-back to the loader threads."""
+        fz = self.pr.fused
+        if fz.host_feed["mode"] == "gpu_pull" and os.environ.get("NNDT_PULL_DRIVER", self.pr.conf.get("host_pull_driver", "graph")) == "graph":
+            return self._run_pull_graphs(rounds)
         if self._runner is None:
             graphs = []
             for b in range(2):
