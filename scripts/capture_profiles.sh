@@ -11,9 +11,13 @@ timeout 300 $NCU --set full --import-source on -k regex:mnist_kernel -s 8 -c 1 -
     python scripts/profile_round.py 8 > gpurun_out/p1.log 2>&1
 timeout 300 $NCU --set full --import-source on -k regex:dinno_update -s 8 -c 1 -o gpurun_out/dinno_update \
     python scripts/profile_round.py 8 > gpurun_out/p2.log 2>&1
-EVAL=1 timeout 300 $NCU --set full --import-source on -k regex:mnist_kernel.*0 -s 0 -c 1 -o gpurun_out/mnist_eval \
-    python scripts/profile_round.py 2 > gpurun_out/p3.log 2>&1
+# validation kernel: 0 training rounds, so the only mnist_kernel launch is the forward-only instantiation
+EVAL=1 timeout 300 $NCU --set full --import-source on -k regex:mnist_kernel -s 0 -c 1 -o gpurun_out/mnist_eval \
+    python scripts/profile_round.py 0 > gpurun_out/p3.log 2>&1
 timeout 300 $NCU --set full --import-source on -k regex:mlp_train_kernel -s 2 -c 1 -o gpurun_out/mlp_train \
     python scripts/profile_mlp.py 4 > gpurun_out/p4.log 2>&1
+# in-kernel phase timing (globaltimer stamps; not under ncu)
+timeout 200 python scripts/profile_round_phases.py --per-step > gpurun_out/phases_per_step.txt 2>&1
+timeout 200 python scripts/profile_round_phases.py > gpurun_out/phases_round_kernel.txt 2>&1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > gpurun_out/smi.csv
 tail -2 gpurun_out/p1.log gpurun_out/p2.log gpurun_out/p3.log gpurun_out/p4.log

@@ -73,8 +73,20 @@ def launches(name):
 
 if __name__ == "__main__":
     launches("launches_mnist")
-    summarize("mnist_train", "mnist_kernel<8,768,train> — fused MNIST conv-net forward+backward, 10 nodes x 8 slices", "")
+    summarize("mnist_train", "mnist_kernel<5,768,train> — fused MNIST conv-net forward+backward, 10 nodes x 13 batch slices (130 CTAs)", "")
     summarize("mnist_eval", "mnist_kernel<8,768,eval> — forward-only validation pass", "")
     summarize("dinno_update", "dinno_update_kernel<float> — fused neighbor pull + dual ascent + prox-gradient + Adam", "")
     summarize("mlp_train", "mlp_train_kernel<256,2> — tcgen05/TMEM FourierNet forward+backward (7 nodes x 12500 rows)", "")
+    ph = []
+    for f, title in (("phases_per_step.txt", "Per-step kernel `mnist_kernel<spb,768,train>` (production path, bench configuration)"),
+                     ("phases_round_kernel.txt", "Opt-in one-launch round kernel `dinno_round_kernel<8,768>` (clusters of 8 CTAs per node)")):
+        p = os.path.join(ROOT, "gpurun_out", f)
+        if os.path.exists(p):
+            body = [l.rstrip() for l in open(p) if l.strip() and not l.startswith(("W0", "/"))]
+            ph += [f"## {title}", "", "```"] + body[-45:] + ["```", ""]
+    if ph:
+        head = ["# In-kernel phase timing (%globaltimer stamps, thread 0 of every CTA, last launch of a 200-round run)", "",
+                "`python scripts/profile_round_phases.py [--per-step]` on one B200, CUDA-graph replay, not under ncu.",
+                "Mean / max over CTAs of the time between consecutive phase boundaries (barriers).", ""]
+        open(os.path.join(OUT, "phase_timing.md"), "w").write("\n".join(head + ph) + "\n")
     print(os.listdir(OUT))
