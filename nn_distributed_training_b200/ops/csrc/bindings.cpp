@@ -80,6 +80,7 @@ static consensus::Common<T> common_from(const py::dict& d) {
   c.flags = ptr<int>(d, "flags"); c.peer_flag = ptr<const int64_t>(d, "peer_flag");
   c.world = geti(d, "world", 1); c.rank = geti(d, "rank", 0);
   c.done_ctr = ptr<unsigned int>(d, "done_ctr"); c.err = ptr<int>(d, "err");
+  c.flags_in_kernel = geti(d, "flags_in_kernel", 1);
   c.sum_mode = geti(d, "sum_mode", 0); c.n_total = geti(d, "n_total", 0);
   c.sum_local = ptr<double>(d, "sum_local"); c.sum_mc = ptr<const double>(d, "sum_mc");
   c.sum_flags = ptr<int>(d, "sum_flags"); c.peer_sum_flag = ptr<const int64_t>(d, "peer_sum_flag");
@@ -103,6 +104,7 @@ struct ConsensusOp {
     check(consensus::launch_dinno_update<T>(dn, cur_stream()), "dinno_update");
   }
   void local_sum() { check(consensus::launch_local_sum<T>(c, cur_stream()), "local_sum"); }
+  void publish() { check(consensus::launch_publish_round<T>(c, cur_stream()), "publish_round"); }
   void dsgd_mix() { check(consensus::launch_dsgd_mix<T>(c, cur_stream()), "dsgd_mix"); }
   void dsgd_step() { check(consensus::launch_dsgd_step<T>(c, cur_stream()), "dsgd_step"); }
   void dsgt_init() { check(consensus::launch_dsgt_init<T>(gt, cur_stream()), "dsgt_init"); }
@@ -116,6 +118,7 @@ static void bind_consensus(py::module& m, const char* name) {
       .def(py::init<const py::dict&>())
       .def("dinno_update", &ConsensusOp<T>::dinno_update)
       .def("local_sum", &ConsensusOp<T>::local_sum)
+      .def("publish", &ConsensusOp<T>::publish)
       .def("dsgd_mix", &ConsensusOp<T>::dsgd_mix)
       .def("dsgd_step", &ConsensusOp<T>::dsgd_step)
       .def("dsgt_init", &ConsensusOp<T>::dsgt_init)

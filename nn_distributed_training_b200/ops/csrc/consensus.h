@@ -47,6 +47,7 @@ struct Common {
   int world, rank;
   unsigned int* done_ctr;     // [1] last-block detection
   int* err;                   // [1] set on spin timeout
+  int flags_in_kernel;        // 1: the round's last kernel announces it to the peers itself; 0: publish_round_kernel does
   // complete-graph ("sum") mode: Metropolis weights are uniform 1/N, so every aggregate is a function of
   // S = sum over ALL nodes.  Each rank reduces its local rows into `sum_local` and the consumers fetch the
   // network-wide sum either with one NVLS in-switch reduction (multimem.ld_reduce over `sum_mc`) or, on a
@@ -79,6 +80,7 @@ template <typename T> cudaError_t launch_dsgt_init(const DsgtArgs<T>& a, cudaStr
 template <typename T> cudaError_t launch_dsgt_mix(const DsgtArgs<T>& a, cudaStream_t st);
 template <typename T> cudaError_t launch_dsgt_track(const DsgtArgs<T>& a, cudaStream_t st);
 template <typename T> cudaError_t launch_local_sum(const Common<T>& c, cudaStream_t st);
+template <typename T> cudaError_t launch_publish_round(const Common<T>& c, cudaStream_t st);
 
 // K6 consensus metric (problems/dist_mnist_problem.py:155-169): distances between L2-normalised parameter rows.
 // rows[j] is the device address of node j's current row (local, or a peer GPU's published row over NVLink).

@@ -59,10 +59,15 @@ NNDT_DEVINL void wait_neighbors(const Common<T>& c, int gid, int l, int k) {
 // last block of the launch: advance the round counter and announce the new round to peers
 template <typename T>
 NNDT_DEVINL void finish_round(const Common<T>& c, int k) {
+  // flags_in_kernel == 0: a separate publish_round_kernel on a forked graph branch announces the round to the
+  // peers (system fence + remote flag stores off the local critical path); this kernel only advances the counter.
+  const bool announce = c.world > 1 && c.flags_in_kernel;
   __shared__ bool is_last;
-  __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
+    // release this block's published rows before arriving (the CTA barrier makes the fence cumulative over every
+    // thread's stores).  Otherwise the kernel boundary is the only consumer-side ordering needed.
+    if (announce) __threadfence();
     const unsigned total = gridDim.x * gridDim.y;
     is_last = (atomicAdd(c.done_ctr, 1u) == total - 1);
   }
@@ -72,7 +77,7 @@ NNDT_DEVINL void finish_round(const Common<T>& c, int k) {
       *c.done_ctr = 0;
       *c.round_ctr = k + 1;
     }
-    if (c.world > 1) {
+    if (announce) {
       __threadfence_system();
       if ((int)threadIdx.x < c.world && (int)threadIdx.x != c.rank)
         st_release_sys(reinterpret_cast<int*>(c.peer_flag[threadIdx.x]), k + 1);

@@ -148,6 +148,18 @@ class ConsensusEngine:
         # published buffer is allocated with the max count, so pass that as the row count of pub
         d["L"] = L
         d["pub_L"] = self.Lpub
+        # multi-GPU: the "round published" flags can be written by publish_round_kernel on a forked graph branch
+        # (round_program.py) instead of the round's last kernel.
+        # Measured (2 GPUs): the fork breaks the PDL edge into the next round's first kernel, which costs the
+        # resident 64-round graphs 2.9 us / round, while the host-fed graphs (already forked per round for the
+        # staging kernel) gain 1.9 us / round -> "auto" enables it only there.
+        sp = opt.conf.get("separate_publish", pr.conf.get("separate_publish", "auto"))
+        if sp == "auto":
+            sp = (pr.fused is not None and pr.conf.get("input_pipeline", "resident") == "host"
+                  and pr.conf.get("host_gather", "gpu_pull") == "gpu_pull"
+                  and pr.conf.get("host_pull_driver", "graph") == "graph")
+        self.separate_publish = bool(ctx.world_size > 1 and sp)
+        d["flags_in_kernel"] = 0 if self.separate_publish else 1
         if pr.fused is not None and getattr(pr, "track_tloss", False) and self.dtype == torch.float32:
             # the kernel that consumes a gradient also folds that step's loss into the EMA tracker
             d.update(loss_part=pr.fused.loss_part.data_ptr(), tloss=pr.tloss_local.data_ptr(),

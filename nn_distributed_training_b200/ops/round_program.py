@@ -31,9 +31,11 @@ def _nvtx(name):
     return torch.cuda.nvtx.range(name)
 
 
-def _round_ops(opt, eng, grads, round_op=None):
+def _round_ops(opt, eng, grads, round_op=None, publish=None):
     with _nvtx(f"consensus_round/{opt.alg_name}"):
         _round_ops_impl(opt, eng, grads, round_op)
+        if eng.separate_publish:
+            (publish or eng.op.publish)()      # announce the round to the peers (forked branch under capture)
 
 
 def _round_ops_impl(opt, eng, grads, round_op=None):
@@ -80,6 +82,8 @@ class RoundProgram:
         self._graphs: Dict[int, torch.cuda.CUDAGraph] = {}
         self.host_mode = False
         self._round_ops = None
+        self._pub_side = None
+        self._pub_pending = False
         if pr.fused is not None:
             pr.fused.sync_calls_from_host()
             if pr.conf.get("input_pipeline", "resident") == "host":
@@ -102,6 +106,23 @@ class RoundProgram:
                     and getattr(pr.fused, "supports_round_kernel", lambda o: False)(opt)):
                 sets = [0, 1] if self.host_mode else [None]
                 self._round_ops = {b: pr.fused.round_op(self.eng._keep, b) for b in sets}
+
+    # ---- peer announcement off the critical path ---------------------------------------------------------------
+    def _publish_forked(self):
+        """Under capture: run publish_round_kernel on a side stream that forks after the round's last kernel, so the
+        system fence + remote flag stores overlap the next round's forward/backward; joined at the end of the graph."""
+        if self._pub_side is None:
+            self._pub_side = torch.cuda.Stream(device=self.pr.device)
+        main = torch.cuda.current_stream(self.pr.device)
+        self._pub_side.wait_stream(main)
+        with torch.cuda.stream(self._pub_side):
+            self.eng.op.publish()
+        self._pub_pending = True
+
+    def _join_publish(self):
+        if self._pub_pending:
+            torch.cuda.current_stream(self.pr.device).wait_stream(self._pub_side)
+            self._pub_pending = False
 
     def round_op(self):
         if self._round_ops is None:
@@ -153,9 +174,10 @@ class RoundProgram:
                 with torch.cuda.stream(side):
                     fz.gather_ops[b ^ 1].launch()
                 self._stage_set = b
-                _round_ops(self.opt, self.eng, self.grads, self.round_op())
+                _round_ops(self.opt, self.eng, self.grads, self.round_op(), self._publish_forked)
                 fz.loss_readback()
                 main.wait_stream(side)     # round i+1 consumes what was just staged (also joins the fork)
+            self._join_publish()
         return g
 
     def _run_pull_graphs(self, rounds: int):
@@ -214,7 +236,8 @@ class RoundProgram:
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):
                         for _ in range(r):
-                            _round_ops(self.opt, self.eng, self.grads, self.round_op())
+                            _round_ops(self.opt, self.eng, self.grads, self.round_op(), self._publish_forked)
+                        self._join_publish()
                     self._graphs[r] = g
                 g.replay()
             else:
