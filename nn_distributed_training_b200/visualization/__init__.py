@@ -1,1 +1,2 @@
 from .results import load_results, summarize_run, rounds_to_threshold, plot_run
+from . import animations  # noqa: E402,F401

@@ -124,6 +124,12 @@ def test_online_density_runner_dynamic_graph(tmp_path, synthetic_dir):
     assert res["train_loss_moving_average"][-1].min() > 0
     models = torch.load(os.path.join(out, "dinno_log_models.pt"), weights_only=False)
     assert set(models) == {0, 1, 2} and "seq.0.linear.weight" in models[0]
+    # density animation (visualization/animations/density_anim.ipynb) from the saved mesh evaluations
+    from nn_distributed_training_b200.visualization import animations
+    frames = animations.density_frames(res, node=1, scale=1)
+    assert len(frames) == 1 and frames[0].size[0] > 10
+    gif = animations.save_gif(frames * 2, os.path.join(str(tmp_path), "d.gif"))
+    assert os.path.getsize(gif) > 100
 
 
 def test_offline_density_runner(tmp_path, synthetic_dir):
@@ -153,6 +159,11 @@ def test_scaling_runner(tmp_path, monkeypatch):
     dist_mnist_scaling.experiment(_write(str(tmp_path), "s.yaml", conf))
     out = glob.glob(os.path.join(str(tmp_path), "*_scaling_dinno_const_fied"))[0]
     assert {"0.gpickle", "1.gpickle", "0_results.pt", "1_results.pt"} <= set(os.listdir(out))
+    # the table behind visualization/scaling_plots.ipynb
+    from nn_distributed_training_b200.visualization.animations import scaling_table
+    rows = scaling_table(out, evaluate_frequency=2, thresholds=(0.0, 2.0))
+    assert [r["trial"] for r in rows] == [0, 1] and all(4 <= r["N"] <= 6 and r["fiedler"] > 0 for r in rows)
+    assert all(r["rounds_to_0"] == 0 and r["rounds_to_200"] is None for r in rows)
 
 
 def test_visualization_summary_and_tools(tmp_path, monkeypatch):
@@ -165,8 +176,20 @@ def test_visualization_summary_and_tools(tmp_path, monkeypatch):
     conf["experiment"].update(output_metadir=str(tmp_path), writeout=True)
     conf["problem_configs"]["problem1"]["optimizer_config"]["outer_iterations"] = 5
     conf["problem_configs"]["problem1"]["metrics_config"]["evaluate_frequency"] = 2
+    conf["problem_configs"]["problem1"]["metrics"] = list(conf["problem_configs"]["problem1"]["metrics"]) + ["validation_as_vector"]
     dist_mnist_ex.experiment(_write(str(tmp_path), "c.yaml", conf))
     run = glob.glob(os.path.join(str(tmp_path), "*_dist_mnist_template"))[0]
+    # animations of visualization/animations/mnist_anim.ipynb: digit grid framed by correctness, accuracy curve
+    from nn_distributed_training_b200.visualization import animations
+    m = load_results(run)["dsgd"]
+    val = M.synthetic_mnist(128, seed=0)
+    frames = animations.mnist_grid_frames(m, val.x.reshape(128, -1), node=1, grid=(4, 5), cell=20, border=2)
+    assert len(frames) == len(m["validation_as_vector"]) and frames[0].size == (100, 80)
+    inds = animations.pick_grid_indices(m["validation_as_vector"], num_total=20)
+    assert inds.numel() == 20 and inds.unique().numel() == 20
+    acc_frames = animations.accuracy_frames(m, evaluate_frequency=2, centralized=0.985)
+    assert len(acc_frames) == len(m["top1_accuracy"])
+    assert os.path.getsize(animations.save_gif(frames, os.path.join(str(tmp_path), "m.gif"))) > 100
     s = summarize_run(run)
     assert "dsgd" in s and 0.0 <= s["dsgd"]["final_top1_mean"] <= 1.0
     r = rounds_to_threshold(load_results(run)["dsgd"], 0.0, 2)
