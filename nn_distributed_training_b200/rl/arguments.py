@@ -10,4 +10,5 @@ def get_args(argv=None):
     p.add_argument("--num_envs", type=int, default=16)
     p.add_argument("--total_timesteps", type=int, default=10_000_000)
     p.add_argument("--device", type=str, default="cpu")
+    p.add_argument("--render", type=str, default="")          # test mode: write a GIF of the first episode here
     return p.parse_args(argv)

@@ -58,8 +58,19 @@ class _ConsensusPPO:
                 profiler.step()
             if k % self.pr.save_freq == 0 and self.conf.get("writeout", True):
                 self.save(k)
+            if getattr(self.pr, "render", False) and k % max(int(self.pr.render_every_i), 1) == 0:
+                self.render_episode(k)
             k += 1
         return
+
+    def render_episode(self, k):
+        """Animated GIF of one episode with every predator running its own current actor (reference:
+        RL/dist_rl/vids/*.mp4, rendered from the pyglet window)."""
+        from .eval_policy import rollout, save_rollout_gif
+        os.makedirs(self.out_dir, exist_ok=True)
+        actors = [self.pr.models[i].actor for i in range(self.pr.N)]
+        _, _, traj = rollout(actors, self.pr.env, record=True)
+        return save_rollout_gif(self.pr.env, traj, os.path.join(self.out_dir, f"{self.alg}_{self.conf.get('ID', 0)}_{k}.gif"))
 
     def save(self, k):
         os.makedirs(self.out_dir, exist_ok=True)

@@ -1,6 +1,6 @@
 """Roll out trained policies and report episodic returns (reference: RL/eval_policy.py and
-RL/dist_rl/eval_policy.py:177-223).  Rendering is replaced by an optional trajectory dump
-(``positions [T, A, 2]``) that the plotting helpers turn into figures/animations."""
+RL/dist_rl/eval_policy.py:177-223).  Rendering: ``record=True`` keeps the positions ``[T, A, 2]`` of world 0 and
+``save_rollout_gif`` turns them into an animation (the reference's pyglet window / vids/*.mp4)."""
 from __future__ import annotations
 
 import numpy as np
@@ -32,10 +32,20 @@ def rollout(actors, env: SimpleTagEnv, record=False):
     return total.cpu().numpy(), t, (np.stack(traj) if record else None)
 
 
-def eval_policy(actors, env: SimpleTagEnv, episodes=5, record=False):
+def save_rollout_gif(env: SimpleTagEnv, traj, out: str, size: int = 400, fps: int = 10) -> str:
+    """Animated GIF of a recorded rollout (``traj [T, A, 2]``)."""
+    frames = [env.render(size=size, pos=p) for p in traj]
+    frames[0].save(out, save_all=True, append_images=frames[1:], duration=max(int(1000 / fps), 20), loop=0)
+    return out
+
+
+def eval_policy(actors, env: SimpleTagEnv, episodes=5, record=False, render_to=None):
+    """``render_to``: path of a GIF of the first episode (implies ``record``)."""
     rets = []
     for ep in range(episodes):
-        ret, length, traj = rollout(actors, env, record=record and ep == 0)
+        ret, length, traj = rollout(actors, env, record=(record or render_to is not None) and ep == 0)
+        if render_to is not None and ep == 0:
+            save_rollout_gif(env, traj, render_to)
         rets.append(ret.mean())
         print(f"-------------------- Episode #{ep} --------------------\nEpisodic Length: {length}\n"
               f"Episodic Return: {ret.mean():.2f}\n------------------------------------------------------", flush=True)

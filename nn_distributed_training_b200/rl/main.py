@@ -32,14 +32,14 @@ def train(env, hyperparameters, actor_model, critic_model, total_timesteps):
     return model
 
 
-def test(env, actor_model):
+def test(env, actor_model, render_to=None):
     if actor_model == "":
         print("Didn't specify model file. Exiting.", flush=True)
         sys.exit(0)
     obs_dim = env.observation_spaces["adversary_0"].shape[0]
     policy = FFReLUNet([obs_dim, 64, 64, 64, 5])
     policy.load_state_dict(torch.load(actor_model, map_location=env.device))
-    return eval_policy(policy.to(env.device), env)
+    return eval_policy(policy.to(env.device), env, render_to=render_to or None)
 
 
 def main(argv=None):
@@ -50,7 +50,7 @@ def main(argv=None):
     if args.mode == "train":
         train(env, hyper, args.actor_model, args.critic_model, args.total_timesteps)
     else:
-        test(env, args.actor_model)
+        test(env, args.actor_model, render_to=args.render)
 
 
 if __name__ == "__main__":

@@ -106,6 +106,16 @@ class PPO:
             self._log_summary()
             if i_so_far % self.save_freq == 0:
                 self.save()
+            if self.render and i_so_far % self.render_every_i == 0:
+                self.render_episode(i_so_far)
+
+    def render_episode(self, i):
+        """``render=True``: an animated GIF of one episode of the current policy every ``render_every_i`` iterations
+        (the reference opens a pyglet window during rollouts, RL/ppo.py:197-199)."""
+        from .eval_policy import rollout, save_rollout_gif
+        os.makedirs(self.out_dir, exist_ok=True)
+        _, _, traj = rollout(self.actor, self.env, record=True)
+        return save_rollout_gif(self.env, traj, os.path.join(self.out_dir, f"render_{self.ID}_{i}.gif"))
 
     def save(self):
         os.makedirs(self.out_dir, exist_ok=True)

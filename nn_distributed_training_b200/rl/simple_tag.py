@@ -121,6 +121,26 @@ class SimpleTagEnv:
         self.cycle += 1
         return (*self._rewards(), self.cycle >= self.max_cycles)
 
+    # ------------------------------------------------------------------
+    def render(self, world: int = 0, size: int = 400, pos=None):
+        """RGB frame of one world (the reference renders through pyglet, _mpe_utils/rendering.py): predators red,
+        prey green, obstacles grey, view [-1.3, 1.3]^2.  ``pos`` overrides the agent positions (recorded rollouts)."""
+        from PIL import Image, ImageDraw
+        im = Image.new("RGB", (size, size), (255, 255, 255))
+        d = ImageDraw.Draw(im)
+        cam = 1.3
+
+        def circle(xy, r, fill):
+            cx, cy = (xy[0] + cam) / (2 * cam) * size, (cam - xy[1]) / (2 * cam) * size
+            rr = r / (2 * cam) * size
+            d.ellipse([cx - rr, cy - rr, cx + rr, cy + rr], fill=fill, outline=(0, 0, 0))
+        for o in self.obst.tolist():
+            circle(o, self.obst_size, (64, 64, 64))
+        p = self.pos[world].tolist() if pos is None else [list(map(float, q)) for q in pos]
+        for i, q in enumerate(p):
+            circle(q, float(self.size[i]), (217, 89, 89) if i < self.n_adv else (89, 217, 89))
+        return im
+
     def _rewards(self):
         adv, good = self.pos[:, : self.n_adv], self.pos[:, self.n_adv:]
         dist = (adv.unsqueeze(2) - good.unsqueeze(1)).norm(dim=-1)    # [E, n_adv, n_good]

@@ -137,3 +137,27 @@ def test_centralized_ppo_and_eval(tmp_path):
     assert (tmp_path / "ppo_actor_tag_7.pth").exists() and len(m.avg_ep_rews) >= 1
     ret = rl_main.test(env, str(tmp_path / "ppo_actor_tag_7.pth"))
     assert np.isfinite(ret)
+
+
+def test_env_render_and_rollout_gif(tmp_path):
+    """Rendering (reference: pyglet window / vids/*.mp4): PIL frames of a world and a GIF of a recorded rollout;
+    ``render=True`` in the trainers writes one every ``render_every_i`` iterations."""
+    import os
+    from nn_distributed_training_b200.rl.eval_policy import rollout, save_rollout_gif
+    from nn_distributed_training_b200.rl.simple_tag import SimpleTagEnv
+    from nn_distributed_training_b200.rl.model import FFReLUNet
+    env = SimpleTagEnv(num_envs=2, num_obstacles=8, max_cycles=6, seed=0)
+    im = env.render(size=120)
+    assert im.size == (120, 120) and len(im.getcolors(maxcolors=1 << 16)) >= 4        # background, obstacles, predators, prey
+    torch.manual_seed(0)
+    actor = FFReLUNet([env.observation_spaces["adversary_0"].shape[0], 16, 5])
+    ret, length, traj = rollout(actor, env, record=True)
+    assert traj.shape == (6, 4, 2) and length == 6
+    out = save_rollout_gif(env, traj, os.path.join(str(tmp_path), "ep.gif"), size=100)
+    assert os.path.getsize(out) > 200
+    from nn_distributed_training_b200.rl.ppo import PPO
+    agent = PPO(FFReLUNet, SimpleTagEnv(num_envs=2, num_obstacles=2, max_cycles=5, seed=1), timesteps_per_batch=20,
+                max_timesteps_per_episode=5, n_updates_per_iteration=1, render=True, render_every_i=1, save_freq=100,
+                out_dir=str(tmp_path), seed=0)
+    agent.learn(total_timesteps=20)
+    assert any(f.startswith("render_0_") and f.endswith(".gif") for f in os.listdir(str(tmp_path)))
