@@ -2,20 +2,19 @@
 //   conv 1->3 5x5 -> ReLU -> maxpool2 -> fc 432->64 -> ReLU -> fc 64->10 -> log-softmax -> NLL
 // for every graph node hosted by this GPU in ONE launch (reference op chain:
 // models/mnist_conv_nn.py:16-25 driven by problems/dist_mnist_problem.py:96-98, where it is
-// ~30 eager ATen/cuDNN launches per node and step).
+// ~30 eager ATen/cuDNN launches per node and step).  The device code lives in mnist_device.cuh.
 //
-// Work decomposition: grid = (S batch slices, L nodes); a CTA owns SPB samples of one node.
-// The 110 KB fc1 weight matrix is staged once per CTA into shared memory with cp.async
-// (row stride padded to 436 floats -> conflict-free 128-bit reads along j), overlapped with
-// the conv+ReLU+pool phase which runs out of an even/odd column-split image tile
-// (conflict-free stride-2 accesses).  Minibatch rows are gathered in-kernel through the
-// stateless Feistel sampler, so there is no host work, no index tensor and no H2D copy per
-// step.  Each CTA writes its slice's partial gradient row; the consensus update kernel that
-// follows sums the S partials while applying the optimizer step (no separate reduce launch).
+// Work decomposition: grid = (S batch slices, L nodes); a CTA of 768 threads owns SPB samples of one node, and the
+// Python side picks SPB (4..8) so that S x L CTAs fill the SMs in one wave.  The 110 KB fc1 weight matrix is
+// staged per CTA by the TMA engine (cp.async.bulk per padded row, mbarrier transaction count) while warp 0 runs
+// the stateless Feistel sampler and the row gather, so there is no host work, no index tensor and no H2D copy per
+// step; conv+ReLU+pool run out of an even/odd column-split image tile; fc1 / da1 / dW1 are mma.sync 3xTF32
+// tensor-core GEMMs (fp32-accurate).  Each CTA writes its slice's partial gradient row; the consensus update
+// kernel that follows sums the S partials while applying the optimizer step (no separate reduce launch).
 //
-// Batch 64 x 28k parameters is far below a tcgen05 tile's break-even (M=64 of a 128-row MMA,
-// K=432; the whole fc1 GEMM is 1.8 MFLOP) — see DESIGN.md §MNIST for the arithmetic; the
-// tensor-core path of this framework is ops/csrc/mlp_tc.cu (Fourier / ReLU MLPs).
+// Batch 64 x 28k parameters is far below a tcgen05 tile's break-even (the whole fc1 GEMM is 1.8 MFLOP, and the
+// fp32-accurate operand split would need two copies of the weight tile in shared memory) — DESIGN.md §3.1; the
+// tcgen05 path of this framework is ops/csrc/mlp_tc.cu (Fourier / ReLU MLPs).
 #include "mnist_device.cuh"
 
 namespace nndt {

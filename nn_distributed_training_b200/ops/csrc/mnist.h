@@ -23,7 +23,7 @@ struct Args {
   const int* shard_len;   // [L]
   int* calls;             // [L] draw counter per node (device); the training kernel advances it itself
   unsigned int* arrive;   // [L] CTA arrival counters used to advance `calls` exactly once per launch
-  int tune;               // bit 0: sampler chain + row gather issued before the PDL wait, bit 1: L2 prefetch of the next draw's rows
+  int tune;               // bit 0: sampler chain + row gather issued before the PDL wait
   long long* prof;        // optional [L*S, 64] %globaltimer stamps (scripts/profile_round_phases.py); nullptr = off
   // training outputs
   float* grad_part;       // [L, S, n_pad]

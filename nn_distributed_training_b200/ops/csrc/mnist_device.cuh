@@ -17,17 +17,11 @@ constexpr int XROW = 22;                // padded row stride of the even/odd col
 constexpr int XPLANE = HW * XROW;       // 616 floats per plane
 constexpr int CGROUP = 256;             // threads cooperating on one conv channel in the backward
 
-// NT threads per CTA: 64 hidden units x (NT/64) k-slices must tile the 108 float4 of an fc1 row.
-template <int NT> struct Geo {
-  static constexpr int KSLICES = NT / 64;
-  static constexpr int K4S = (FC1_IN / 4) / KSLICES;
-  static_assert((FC1_IN / 4) % KSLICES == 0, "NT/64 must divide 108");
-  static_assert(NT >= 3 * CGROUP && NT >= FC1_IN, "need >= 768 threads");
-};
-
+// NT = 768 threads per CTA: 24 warps = 4 row tiles x 6 k-groups of the fc1-sized MMAs, >= 3 x CGROUP for the conv
+// backward and >= FC1_IN for the element-wise phases.
 template <int SPB, int NT>
 struct Smem {
-  float w1[HID * W1_STRIDE];            // fc1 weights; later scratch for dW1 transposition / conv-grad reduce
+  float w1[HID * W1_STRIDE];            // fc1 weights; later scratch for the conv-grad reduce
   float xe[SPB * XPLANE];
   float xo[SPB * XPLANE];
   float a1[8 * A1_STRIDE];              // fc1 input [sample][k]; rows >= SPB stay zero (K / N padding of the MMAs)
@@ -100,12 +94,6 @@ __device__ __forceinline__ void commit_images(Smem<SPB, NT>& sm, const Args& a, 
       e[0] = v0; d[0] = v1; e[1] = v2; d[1] = v3;
     }
   }
-}
-
-// pixel (r, c) of sample s
-template <int SPB, int NT>
-__device__ __forceinline__ float px(const Smem<SPB, NT>& sm, int s, int r, int c) {
-  return ((c & 1) ? sm.xo : sm.xe)[s * XPLANE + r * XROW + (c >> 1)];
 }
 
 template <int SPB, int NT>
@@ -359,21 +347,6 @@ __device__ __forceinline__ void compute_chunk(Smem<SPB, NT>& sm, const Args& a, 
     }
     __syncthreads();
     phase_stamp(prof, 5, tid);
-    if (TRAIN && (a.tune & 2) && !a.direct && tid >= 64 && tid < 64 + SPB * 8) {
-      // warps 2+ idle through the 8-thread softmax: pull the rows of this slice's NEXT draw into L2
-      const int s = (tid - 64) >> 3, line = (tid - 64) & 7;        // 784 B (u8) = 7 x 128 B lines per row
-      const BatchLoc loc = locate_batch((uint32_t)(bg.call + 1), bg.m, (uint32_t)a.batch);
-      const uint32_t t = slice * SPB + s;
-      if (t < loc.size) {
-        const uint32_t key = mix_key((uint32_t)a.seed, (uint32_t)(a.node0 + l), loc.epoch);
-        const size_t idx = (size_t)bg.shard_off + feistel_permute(loc.start + t, bg.m, key);
-        const size_t row_bytes = a.x_is_u8 ? 784 : 784 * 4;
-        const char* row = reinterpret_cast<const char*>(a.x) + idx * row_bytes;
-        for (size_t o = (size_t)line * 128; o < row_bytes; o += 1024)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
-        if (line == 7) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.y + idx));
-      }
-    }
     if (tid < SPB) {
       const int s = tid;
       float mx = sm.z[s * 16];

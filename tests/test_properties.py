@@ -254,3 +254,18 @@ def test_round_timer_as_profiler_hook():
     t = RoundTimer(warmup=2)
     DSGD(pr, "cpu", conf).train(profiler=t)
     assert t.ms_per_round() is not None and t.ms_per_round() > 0
+
+
+def test_choose_spb_fills_one_wave():
+    """Samples per training CTA: smallest value whose L x ceil(B / spb) CTAs fit in one wave of the SMs."""
+    from nn_distributed_training_b200.ops.mnist_fused import SPB, choose_spb
+    assert choose_spb(64, 10, 148) == 5          # bench configuration: 13 slices x 10 nodes = 130 CTAs
+    assert choose_spb(64, 1, 148) == 4
+    assert choose_spb(64, 18, 148) == 8          # 8 x 18 = 144
+    assert choose_spb(64, 40, 148) == SPB        # nothing fits: fewest CTAs
+    for B in (16, 32, 64, 100):
+        for L in (1, 3, 10, 18, 30):
+            spb = choose_spb(B, L, 148)
+            assert 4 <= spb <= SPB
+            if spb > 4:                          # a smaller value would not have fitted
+                assert L * -(-B // (spb - 1)) > 148
