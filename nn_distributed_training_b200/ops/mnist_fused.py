@@ -189,8 +189,8 @@ class FusedMnist:
         # a training CTA fills an SM's register file (768 threads x 80 registers): a staging block that lands on
         # an SM evicts a training CTA into a second wave, so the staging grid is sized to the SMs left over
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        free = sms - (self.L * self.S) % sms if (self.L * self.S) % sms else 0
-        gather_blocks = int(os.environ.get("NNDT_GATHER_BLOCKS", "0")) or max(4, min(24, free - 2))
+        free = sms - self.L * self.S if self.L * self.S <= sms else 0      # multi-wave grids leave no SM idle
+        gather_blocks = int(os.environ.get("NNDT_GATHER_BLOCKS", "0")) or max(8, min(24, free - 2))
         self.direct_ops, self.gather_ops = [], []
         for b in range(2):
             ops = []
