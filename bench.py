@@ -196,14 +196,13 @@ def run_ours(args):
         return float(ctx.all_reduce_max(t).item())
 
     # ---------------- device-timed, resident shards ----------------------------
-    pr = build_problem(ctx, n_nodes, opt_conf(oits), eval_every=10 ** 9)
+    pipeline = os.environ.get("NNDT_BENCH_PIPELINE", "auto")      # auto (= staged-resident) | resident (A/B switch)
+    pr = build_problem(ctx, n_nodes, opt_conf(oits), eval_every=10 ** 9, extra={"input_pipeline": pipeline})
     opt = DiNNO(pr, dev, pr.conf["optimizer_config"])
-    chunk = min(K, 64)
-    rem = K % chunk
-    opt.run_rounds(max(W, 3))            # warm-up (captures the graphs used below)
-    opt.run_rounds(chunk)
-    if rem:
-        opt.run_rounds(rem)
+    opt.run_rounds(max(W, 3))            # warm-up
+    n_warm = 2 if K % 2 else 1           # an untimed pass with the timed call's chunking (and staging parity): every
+    for _ in range(n_warm):              # CUDA graph the timed region replays is captured here
+        opt.run_rounds(K)
     sampler = ClockSampler(dev.index or 0)
     torch.cuda.synchronize()
     ctx.barrier()
@@ -217,6 +216,7 @@ def run_ours(args):
     clocks = sampler.stop()
     ms = maxreduce(e0.elapsed_time(e1))
     launches = K * opt._program.launches_per_round()
+    opt_pipeline = opt._program.pipeline + (" (HBM-resident shards; the staging kernel gathers the next round's rows)" if opt._program.pipeline == "staged" else "")
     round_kernel = "dinno_round_kernel (1 cluster launch/round)" if opt._program.round_op() is not None else "mnist_kernel + dinno_update_kernel per primal step"
     # model quality after the rounds run so far (not timed)
     pr.evaluate_metrics()
@@ -266,7 +266,7 @@ def run_ours(args):
         out = {
             "metric": "consensus node-rounds/sec (DiNNO, dist_mnist_PAPER; rounds/sec x graph nodes)",
             "value": n_nodes * K / (ms / 1e3), "unit": "node-rounds/s", "n_gpus": args.gpus, "steps": K,
-            "warmup": max(W, 3) + chunk + rem, "ms_per_step": ms / K, "higher_is_better": True,
+            "warmup": max(W, 3) + n_warm * K, "ms_per_step": ms / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
             "impl": "ours",
             "config": {"model": "MNISTConvNet(3,5,64) 28440 params", "yaml": "dist_mnist_PAPER.yaml/problem1 (DiNNO)",
@@ -274,6 +274,7 @@ def run_ours(args):
                        "primal_iterations": PITS, "seq_len": None, "parallelism": f"consensus graph, {NODES_PER_GPU} nodes/GPU x {args.gpus} GPU",
                        "rounds_per_sec": K / (ms / 1e3), "eval": "excluded from timed region", "kernels": round_kernel,
                        "l2": f"inputs {NODES_PER_GPU * SAMPLES_PER_NODE * 784 / 1e6:.0f} MB/GPU > L2, random row gather; no flush",
+                       "input_pipeline": opt_pipeline,
                        "compute": "fp32 CUDA-core fused fwd/bwd + fused consensus kernels (reference runs fp64)",
                        "exchange": f"in-kernel P2P pulls of neighbor rows ({symm_how} peer mapping); no NCCL on the hot path"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,

@@ -6,6 +6,7 @@ sequence is captured in a CUDA graph and replayed (``round_program.py``).
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List
 
 import numpy as np
@@ -19,7 +20,7 @@ OPT_CODE = {"sgd": 0, "adam": 1, "adamw": 2}
 
 
 class ConsensusEngine:
-    def __init__(self, opt, graphs_per_round: List):
+    def __init__(self, opt, graphs_per_round: List, forked_graphs: bool = False):
         self.opt = opt
         pr = self.pr = opt.pr
         self.ext = load_ext(required=True)
@@ -155,9 +156,7 @@ class ConsensusEngine:
         # staging kernel) gain 1.9 us / round -> "auto" enables it only there.
         sp = opt.conf.get("separate_publish", pr.conf.get("separate_publish", "auto"))
         if sp == "auto":
-            sp = (pr.fused is not None and pr.conf.get("input_pipeline", "resident") == "host"
-                  and pr.conf.get("host_gather", "gpu_pull") == "gpu_pull"
-                  and pr.conf.get("host_pull_driver", "graph") == "graph")
+            sp = forked_graphs
         self.separate_publish = bool(ctx.world_size > 1 and sp)
         d["flags_in_kernel"] = 0 if self.separate_publish else 1
         if pr.fused is not None and getattr(pr, "track_tloss", False) and self.dtype == torch.float32:

@@ -130,8 +130,8 @@ class FusedMnist:
         the current round computes — no CPU work per round.
         ``mode="cpu_loader"``: native loader threads (csrc/runtime.cpp) assemble rounds into a
         ring of pinned slots and the runner issues one ``cudaMemcpyAsync`` per round."""
-        if mode == "gpu_pull":
-            return self._enable_gpu_pull(steps_per_round)
+        if mode in ("gpu_pull", "staged"):
+            return self._enable_gpu_pull(steps_per_round, source="device" if mode == "staged" else "host")
         pr, dev = self.pr, self.pr.device
         P, L, B = int(steps_per_round), self.L, self.B
         xb = 1 if self.x_is_u8 else 4
@@ -169,12 +169,19 @@ class FusedMnist:
                               d2h_bytes=L * self.S * 4)
         return self.host_feed
 
-    def _enable_gpu_pull(self, steps_per_round: int):
+    def _enable_gpu_pull(self, steps_per_round: int, source: str = "host"):
+        """``source="host"``: rows come out of the pinned host copy of the dataset (PCIe).  ``source="device"``
+        (``input_pipeline: staged``): the same staging kernel gathers the next round's rows from the HBM-resident
+        shards into the compact staging set, so the training kernel never runs the sampler chain or a random HBM
+        gather on its critical path."""
         pr, dev = self.pr, self.pr.device
         P, L, B = int(steps_per_round), self.L, self.B
         xb = 1 if self.x_is_u8 else 4
-        self.host_x = self.x.cpu().contiguous().pin_memory()
-        self.host_y = self.y.cpu().contiguous().pin_memory()
+        if source == "host":
+            self.host_x = self.x.cpu().contiguous().pin_memory()
+            self.host_y = self.y.cpu().contiguous().pin_memory()
+        else:
+            self.host_x, self.host_y = self.x, self.y
         self.x_stage = torch.zeros(2, P, L, B, 784, dtype=self.x.dtype, device=dev)
         self.y_stage = torch.zeros(2, P, L, B, dtype=torch.int64, device=dev)
         self.bs_stage = torch.zeros(2, P, L, dtype=torch.int32, device=dev)
@@ -182,6 +189,8 @@ class FusedMnist:
         # result read-back: "mirror" = the training kernel stores each step's losses straight into this pinned host
         # buffer over PCIe (no copy node on the round's critical path); "memcpy" = a D2H copy node per round
         self.loss_mode = str(pr.conf.get("host_loss", os.environ.get("NNDT_HOST_LOSS", "mirror")))
+        if source == "device":
+            self.loss_mode = "none"          # nothing crosses PCIe in the staged-resident pipeline
         pl = pr.placement
         self.calls0 = torch.as_tensor(pr.calls[pl.lo: pl.lo + pl.L].astype(np.int32), device=dev)
         self.stage_round = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -210,8 +219,9 @@ class FusedMnist:
                 calls0=self.calls0.data_ptr(), stage_round=self.stage_round.data_ptr(),
                 done_ctr=self.stage_done.data_ptr(), max_blocks=gather_blocks)))
         self.loader = None
-        self.host_feed = dict(P=P, nslots=2, mode="gpu_pull",
-                              h2d_bytes=P * L * B * (784 * xb + 8), d2h_bytes=L * self.S * 4)
+        self.host_feed = dict(P=P, nslots=2, mode="gpu_pull", source=source,
+                              h2d_bytes=P * L * B * (784 * xb + 8) if source == "host" else 0,
+                              d2h_bytes=L * self.S * 4 if source == "host" else 0)
         return self.host_feed
 
     def make_pull_runner(self, round_graphs):
@@ -245,7 +255,7 @@ class FusedMnist:
     def loss_readback(self):
         """Enqueue the D2H read of the round's per-node losses (nothing to enqueue when the kernel mirrors them
         into the pinned host buffer itself)."""
-        if getattr(self, "loss_mode", "memcpy") != "mirror":
+        if getattr(self, "loss_mode", "memcpy") == "memcpy":
             self.loss_host.copy_(self.loss_part, non_blocking=True)
 
     # ---- validation ---------------------------------------------------------

@@ -74,25 +74,41 @@ class RoundProgram:
         init_draws = 1 if (opt.alg_name == "dsgt" and opt.init_grads and not opt._initialised) else 0
         graphs = pr.plan_graphs(opt.oits, opt.k, self.dpr, init_draws,
                                 refresh=getattr(opt, "refresh_graph", True))
-        self.eng = ConsensusEngine(opt, graphs)
+        self.capturable = pr.fused is not None and os.environ.get("NNDT_NO_GRAPH", "0") != "1"
+        # ---- input pipeline of the fused MNIST problem (decided first: the engine's peer-announcement mode depends on
+        #      whether the rounds run in forked multi-round graphs) -----------------------------------------------------
+        pipeline = "resident"
+        if pr.fused is not None:
+            pipeline = pr.conf.get("input_pipeline", "auto")
+            can_stage = hasattr(pr.fused, "enable_host_feed") and self.capturable and not init_draws
+            if pipeline == "auto":
+                # staged-resident is the faster way to run resident shards (4 % on the headline round): the training
+                # kernel reads a compact, L2-resident batch instead of chasing the sampler through HBM
+                pipeline = "staged" if can_stage else "resident"
+            if not hasattr(pr.fused, "enable_host_feed"):
+                pipeline = "resident"
+        forked = (pipeline == "staged" or (pipeline == "host" and pr.conf.get("host_gather", "gpu_pull") == "gpu_pull")) \
+            and os.environ.get("NNDT_PULL_DRIVER", pr.conf.get("host_pull_driver", "graph")) == "graph"
+        self.eng = ConsensusEngine(opt, graphs, forked_graphs=forked)
         self.graph_plan = graphs
         # evaluation between rounds can use the fused consensus-metric kernel on the published rows
         pr._metric_engine = (self.eng, lambda: opt.k)
-        self.capturable = pr.fused is not None and os.environ.get("NNDT_NO_GRAPH", "0") != "1"
         self._graphs: Dict[int, torch.cuda.CUDAGraph] = {}
         self.host_mode = False
         self._round_ops = None
+        self.pipeline = "resident"
         self._pub_side = None
         self._pub_pending = False
         if pr.fused is not None:
             pr.fused.sync_calls_from_host()
-            if pr.conf.get("input_pipeline", "resident") == "host":
+            if pipeline in ("host", "staged") and hasattr(pr.fused, "enable_host_feed"):
                 if init_draws:
-                    raise NotImplementedError("host-fed pipeline with DSGT init_grads")
+                    raise NotImplementedError("host-fed / staged pipeline with DSGT init_grads")
                 pr.fused.enable_host_feed(self.dpr, nslots=int(pr.conf.get("host_slots", 4)),
                                           threads=int(pr.conf.get("host_threads", 4)),
-                                          mode=pr.conf.get("host_gather", "gpu_pull"))
+                                          mode="staged" if pipeline == "staged" else pr.conf.get("host_gather", "gpu_pull"))
                 self.host_mode = True
+                self.pipeline = pipeline
                 self._runner = None
                 self._stage_set = 0
                 self._pull_graphs: Dict = {}
@@ -130,8 +146,13 @@ class RoundProgram:
         return self._round_ops[self._stage_set if self.host_mode else None]
 
     def launches_per_round(self) -> int:
-        """Kernel launches of one communication round (excluding the host-feed staging kernel)."""
+        """Kernel launches of one communication round (the staging kernel of the host-fed / staged pipelines and the
+        forked peer announcement included)."""
         n = 1 if self.eng.sum_mode else 0
+        if self.host_mode and self.pr.fused.host_feed["mode"] == "gpu_pull":
+            n += 1
+        if self.eng.separate_publish:
+            n += 1
         if self._round_ops is not None:
             return n + 1
         return n + (2 * self.opt.pits if self.opt.alg_name == "dinno" else 3)

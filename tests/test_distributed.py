@@ -26,7 +26,7 @@ def test_gloo_two_ranks_match_single_process(graph):
 
 @pytest.mark.gpu
 @pytest.mark.multigpu
-@pytest.mark.parametrize("graph,pipeline", [("cycle", "resident"), ("complete", "resident"), ("cycle", "host")])
+@pytest.mark.parametrize("graph,pipeline", [("cycle", "auto"), ("complete", "resident"), ("cycle", "host")])
 def test_nccl_peer_mapped_ranks_match_single_process(graph, pipeline):
     """``host``: rows pulled from pinned host memory by the staging kernel inside multi-round graphs, peers
     announced by publish_round_kernel on a forked branch; the single-process oracle uses resident shards."""
@@ -36,5 +36,5 @@ def test_nccl_peer_mapped_ranks_match_single_process(graph, pipeline):
     nproc = 2
     r = _launch(nproc, ["--cuda", "1", "--nodes", "6", "--graph", graph, "--pipeline", pipeline], 29612)
     assert "DIST_RESULT PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
-    if pipeline == "host":
+    if pipeline in ("host", "auto"):      # auto = staged-resident multi-round graphs for DiNNO / DSGD
         assert "separate_publish=True" in r.stdout

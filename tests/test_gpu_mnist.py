@@ -181,16 +181,16 @@ def test_consensus_kernels_fp64_with_autograd_model():
     assert bad.double().mean().item() < 1e-3
 
 
-@pytest.mark.parametrize("mode", ["gpu_pull", "cpu_loader"])
+@pytest.mark.parametrize("mode", ["gpu_pull", "cpu_loader", "staged"])
 def test_host_fed_pipeline_matches_resident(mode):
-    """Host-fed rounds (inputs cross PCIe every round) must train exactly like the resident pipeline:
-    both draw the same rows from the same stateless sampler."""
+    """Host-fed rounds (inputs cross PCIe every round) and staged-resident rounds (same staging kernel, HBM source)
+    must train exactly like the resident pipeline: all draw the same rows from the same stateless sampler."""
     outs = []
-    for pipeline in ("resident", "host"):
+    for pipeline in ("resident", "staged" if mode == "staged" else "host"):
         conf = dict(DINNO, outer_iterations=12)
         pr = _problem(4, 32, "fused", conf, M=100, eval_every=1000)   # 100/32: partial batches + epoch wrap
         pr.conf["input_pipeline"] = pipeline
-        pr.conf["host_gather"] = mode
+        pr.conf["host_gather"] = mode if mode != "staged" else "gpu_pull"
         opt = DiNNO(pr, DEV, conf)
         opt.run_rounds(5)
         opt.run_rounds(4)
