@@ -76,10 +76,32 @@ def validate_optimizer(conf: Dict[str, Any], path: str = "optimizer_config") -> 
     return c
 
 
+# extension keys of a problem config (absent from the reference's schema) and their legal values
+PROBLEM_CHOICES = {
+    "input_pipeline": ("auto", "resident", "staged", "host"),
+    "host_gather": ("gpu_pull", "cpu_loader"),
+    "host_pull_driver": ("graph", "runner"),
+    "host_loss": ("mirror", "memcpy"),
+}
+
+
+def _check_extensions(c: Dict[str, Any], path: str) -> None:
+    for k, legal in PROBLEM_CHOICES.items():
+        if k in c and c[k] not in legal:
+            raise ConfigError(f"{path}.{k} must be one of {'|'.join(legal)} (got {c[k]!r})")
+    if "samples_per_cta" in c and not (c["samples_per_cta"] == 0 or 4 <= int(c["samples_per_cta"]) <= 8):
+        raise ConfigError(f"{path}.samples_per_cta must be 0 (automatic) or 4..8")
+    f = c.get("fault_injection")
+    if f is not None:
+        if not isinstance(f, dict) or not 0.0 <= float(f.get("link_drop_prob", 0.0)) <= 1.0:
+            raise ConfigError(f"{path}.fault_injection needs link_drop_prob in [0, 1]")
+
+
 def validate_problem(conf: Dict[str, Any], path: str, kind: str) -> Dict[str, Any]:
     c = _fill(conf, {"problem_name": REQUIRED, "train_batch_size": REQUIRED, "val_batch_size": REQUIRED,
                      "metrics": REQUIRED, "metrics_config": REQUIRED, "optimizer_config": REQUIRED,
                      "verbose_evals": True}, path)
+    _check_extensions(c, path)
     allowed = MNIST_METRICS if kind == "mnist" else DENSITY_METRICS
     for m in c["metrics"]:
         if m not in allowed:

@@ -45,6 +45,18 @@ def test_config_errors_are_explicit():
     # the README's legacy names still load
     c = validate_optimizer({"alg_name": "cadmm", "rho": 0.5, "primal_lr": 1e-3, "outer_iterations": 3, "primal_iterations": 1})
     assert c["alg_name"] == "dinno" and c["rho_init"] == 0.5 and c["lr_decay_type"] == "constant"
+    # extension keys are checked too
+    from nn_distributed_training_b200.utils.config import validate_problem
+    base = {"problem_name": "p", "train_batch_size": 8, "val_batch_size": 8, "metrics": ["validation_loss"],
+            "metrics_config": {"evaluate_frequency": 1},
+            "optimizer_config": {"alg_name": "dsgd", "alpha0": 0.1, "mu": 0.0, "outer_iterations": 2}}
+    assert validate_problem(dict(base, input_pipeline="staged", samples_per_cta=5), "p", "mnist")["input_pipeline"] == "staged"
+    with pytest.raises(ConfigError, match="input_pipeline"):
+        validate_problem(dict(base, input_pipeline="disk"), "p", "mnist")
+    with pytest.raises(ConfigError, match="samples_per_cta"):
+        validate_problem(dict(base, samples_per_cta=12), "p", "mnist")
+    with pytest.raises(ConfigError, match="fault_injection"):
+        validate_problem(dict(base, fault_injection={"link_drop_prob": 1.5}), "p", "mnist")
 
 
 def test_mnist_template_runs_and_writes_reference_layout(tmp_path, monkeypatch):
