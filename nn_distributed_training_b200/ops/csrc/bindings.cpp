@@ -81,6 +81,7 @@ static consensus::Common<T> common_from(const py::dict& d) {
   c.world = geti(d, "world", 1); c.rank = geti(d, "rank", 0);
   c.done_ctr = ptr<unsigned int>(d, "done_ctr"); c.err = ptr<int>(d, "err");
   c.flags_in_kernel = geti(d, "flags_in_kernel", 1);
+  c.pub_seq = ptr<int>(d, "pub_seq"); c.nbr_seq = ptr<const int64_t>(d, "nbr_seq");
   c.sum_mode = geti(d, "sum_mode", 0); c.n_total = geti(d, "n_total", 0);
   c.sum_local = ptr<double>(d, "sum_local"); c.sum_mc = ptr<const double>(d, "sum_mc");
   c.sum_flags = ptr<int>(d, "sum_flags"); c.peer_sum_flag = ptr<const int64_t>(d, "peer_sum_flag");

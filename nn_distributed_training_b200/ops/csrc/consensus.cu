@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(THREADS) dinno_update_kernel(const DinnoArgs<T
   }
   if (!waited) { pdl_wait(); pdl_launch_dependents(); }
   step_bookkeeping(c, l);
-  if (last) finish_round(c, ri.k);
+  if (last) { tag_published(c, l, ri.k); finish_round(c, ri.k); }
 }
 
 // ------------------------------------------------------------------- DSGD ----
@@ -199,6 +199,7 @@ __global__ void __launch_bounds__(THREADS) dsgd_step_kernel(const Common<T> c) {
     stv(pub_row(c, ri.par ^ 1, 0, l) + i, th);
   }
   step_bookkeeping(c, l);
+  tag_published(c, l, ri.k);
   finish_round(c, ri.k);
 }
 
@@ -298,6 +299,7 @@ __global__ void __launch_bounds__(THREADS) dsgt_track_kernel(const DsgtArgs<T> a
     stv(pub_row(c, ri.par ^ 1, 0, l) + i, ldv(c.theta + row + i));
   }
   step_bookkeeping(c, l);
+  tag_published(c, l, ri.k);
   finish_round(c, ri.k);
 }
 

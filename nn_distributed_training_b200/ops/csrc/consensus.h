@@ -46,7 +46,11 @@ struct Common {
   const int64_t* peer_flag;   // [world] address of *their* slot for this rank
   int world, rank;
   unsigned int* done_ctr;     // [1] last-block detection
-  int* err;                   // [1] set on spin timeout
+  int* err;                   // [1] 1 = spin timeout, 2 = sequence check failed
+  // optional debug build of the protocol: every published row carries the round it belongs to and every
+  // neighbor read verifies it (nullptr = off)
+  int* pub_seq;               // [2 parity, pub_L] local tags, written with the published rows
+  const int64_t* nbr_seq;     // [G, L, dmax, 2] device addresses of the neighbors' tags per parity
   int flags_in_kernel;        // 1: the round's last kernel announces it to the peers itself; 0: publish_round_kernel does
   // complete-graph ("sum") mode: Metropolis weights are uniform 1/N, so every aggregate is a function of
   // S = sum over ALL nodes.  Each rank reduces its local rows into `sum_local` and the consumers fetch the

@@ -38,22 +38,34 @@ NNDT_DEVINL RoundInfo<T> round_info(const Common<T>& c) {
   return r;
 }
 
-// wait until every rank owning a neighbor of local node l has published round k
+// wait until every rank owning a neighbor of local node l has published round k; with the sequence check enabled,
+// also verify that the row about to be read is tagged with round k
 template <typename T>
 NNDT_DEVINL void wait_neighbors(const Common<T>& c, int gid, int l, int k) {
-  if (c.world > 1) {
+  const bool check = c.nbr_seq != nullptr;
+  if (c.world > 1 || check) {
     const int d = c.deg[gid * c.L + l];
     if ((int)threadIdx.x < d) {
-      const int r = c.nbr_rank[(gid * c.L + l) * c.dmax + threadIdx.x];
+      const int r = c.world > 1 ? c.nbr_rank[(gid * c.L + l) * c.dmax + threadIdx.x] : -1;
       if (r >= 0) {
         const long long t0 = clock64();
         while (ld_acquire_sys(c.flags + r) < k) {
           if (clock64() - t0 > kSpinLimit) { *c.err = 1; break; }
         }
       }
+      if (check) {
+        const int* tag = reinterpret_cast<const int*>(c.nbr_seq[((size_t)(gid * c.L + l) * c.dmax + threadIdx.x) * 2 + (k & 1)]);
+        if (ld_acquire_sys(tag) != k) *c.err = 2;
+      }
     }
     __syncthreads();
   }
+}
+
+// tag the rows published for round k + 1 (one thread per node, before the launch's arrival counter)
+template <typename T>
+NNDT_DEVINL void tag_published(const Common<T>& c, int l, int k) {
+  if (c.pub_seq != nullptr && blockIdx.x == 0 && threadIdx.x == 0) c.pub_seq[((k + 1) & 1) * c.pub_L + l] = k + 1;
 }
 
 // last block of the launch: advance the round counter and announce the new round to peers

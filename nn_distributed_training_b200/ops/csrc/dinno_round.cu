@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(NT, 1) dinno_round_kernel(const RoundArgs ra) 
     }
   }
   if (slice == 0 && tid == 0 && ra.m.calls != nullptr) ra.m.calls[l] = calls0 + pits;
+  tag_published(c, l, ri.k);      // blockIdx.x == 0 is slice 0
   finish_round(c, ri.k);
   stamp(prof, cta, 63, tid);
 }

@@ -35,10 +35,13 @@ class ConsensusEngine:
         self.pub_buf = SymmetricBuffer((2, self.C, Lmax, n_pad), self.dtype, ctx)
         self.pub = self.pub_buf.local
         self.Lpub = Lmax
-        self.pub[0, 0, :L].copy_(a.theta)
+        k0 = opt.k
+        # round k0 (0, or the round a checkpoint resumed at) is "published" in the parity it will be read from
+        self.pub[k0 & 1, 0, :L].copy_(a.theta)
+        if opt.alg_name == "dsgt" and getattr(opt, "_initialised", False):
+            self.pub[k0 & 1, 1, :L].copy_(opt.y)
 
         # ---- schedules ----------------------------------------------------------
-        k0 = opt.k
         rho = np.zeros(oits); lr = np.zeros(oits); alpha = np.zeros(oits)
         if opt.alg_name == "dinno":
             rho[:] = [opt.rho_at(k) for k in range(oits)]
@@ -91,6 +94,22 @@ class ConsensusEngine:
         self.t_deg = torch.as_tensor(deg, device=dev)
         self.t_nbr_rank = torch.as_tensor(nbr_rank, device=dev)
         self.t_gid = torch.as_tensor(gid, device=dev)
+
+        # ---- optional protocol self-check: published rows carry their round, neighbor reads verify it ----
+        self.seq_buf = None
+        self.t_nbr_seq = None
+        if opt.conf.get("debug_sequence_check", False) or os.environ.get("NNDT_SEQ_CHECK") == "1":
+            self.seq_buf = SymmetricBuffer((2, Lmax), torch.int32, ctx)
+            self.seq_buf.local.fill_(k0 - 1)
+            self.seq_buf.local[k0 & 1].fill_(k0)
+            nbr_seq = np.zeros((G, L, dmax, 2), dtype=np.int64)
+            for gi, t in enumerate(topos):
+                for l, g in enumerate(pl.local_nodes):
+                    for e, j in enumerate(t.neighbors_noself[g]):
+                        r, lj = int(pl.node_rank[j]), int(pl.node_local[j])
+                        for par in range(2):
+                            nbr_seq[gi, l, e, par] = self.seq_buf.peer_ptrs[r] + (par * Lmax + lj) * 4
+            self.t_nbr_seq = torch.as_tensor(nbr_seq, device=dev)
 
         # ---- counters / flags -----------------------------------------------------
         self.round_ctr = torch.full((1,), k0, dtype=torch.int32, device=dev)
@@ -164,6 +183,8 @@ class ConsensusEngine:
             d.update(loss_part=pr.fused.loss_part.data_ptr(), tloss=pr.tloss_local.data_ptr(),
                      tdecay=float(pr.tloss_decay), loss_S=int(pr.fused.loss_part.shape[1]))
             pr.fused.ema_in_kernel = True
+        if self.seq_buf is not None:
+            d.update(pub_seq=self.seq_buf.local.data_ptr(), nbr_seq=self.t_nbr_seq.data_ptr())
         if self.sum_mode:
             d.update(sum_mode=1, n_total=pr.N, sum_local=self.sum_buf.local.data_ptr(), sum_mc=sum_mc,
                      sum_flags=self.sum_flag_buf.local.data_ptr(), peer_sum_flag=self.t_peer_sum_flag.data_ptr())
@@ -206,5 +227,8 @@ class ConsensusEngine:
         return d_all, d_mean
 
     def check(self):
-        if int(self.err.item()) != 0:
+        e = int(self.err.item())
+        if e == 2:
+            raise RuntimeError("sequence check failed: a neighbor row was read that is not tagged with the current round")
+        if e != 0:
             raise RuntimeError("consensus kernel timed out waiting for a peer's published round")

@@ -218,3 +218,46 @@ def test_fused_consensus_metric_matches_torch():
     ra, rm = consensus_ref.consensus_error(pr.all_theta().double())
     torch.testing.assert_close(a, ra.cpu(), rtol=1e-5, atol=1e-7)
     torch.testing.assert_close(m, rm.cpu(), rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("cls,conf", [(DiNNO, dict(DINNO, persistant_primal_opt=True, outer_iterations=6)),
+                                      (DSGD, dict(DSGD_C, outer_iterations=6)), (DSGT, dict(DSGT_C, outer_iterations=6))])
+def test_fused_checkpoint_resume_is_bit_exact(tmp_path, cls, conf):
+    """Crash after an ODD round (the published rows of the resumed round live in parity 1), resume in a fresh
+    problem/optimizer on the fused path: parameters equal the uninterrupted run bit for bit."""
+    from nn_distributed_training_b200.parallel.context import DistContext
+    from nn_distributed_training_b200.utils import checkpoint as ckpt
+    full = _problem(4, 32, "fused", conf, M=100)
+    cls(full, DEV, copy.deepcopy(conf)).train()
+    first = _problem(4, 32, "fused", conf, M=100)
+    o1 = cls(first, DEV, copy.deepcopy(conf))
+    ckpt.attach(o1, str(tmp_path), "run", every=3, ctx=DistContext.single(torch.device(DEV)))
+    o1.oits = 3                      # "crash" after round 3
+    o1.train()
+    assert o1.k == 3
+    second = _problem(4, 32, "fused", conf, M=100)
+    o2 = cls(second, DEV, copy.deepcopy(conf))
+    ckpt.attach(o2, str(tmp_path), "run", every=3, ctx=DistContext.single(torch.device(DEV)), resume=True)
+    assert o2.k == 3
+    o2.train()
+    assert torch.equal(second.arena.theta, full.arena.theta)
+    assert second.forward_cnt == full.forward_cnt
+
+
+@pytest.mark.parametrize("cls,conf", [(DiNNO, DINNO), (DSGT, DSGT_C)])
+def test_sequence_check_passes_and_detects_stale_rows(cls, conf):
+    """``debug_sequence_check``: every published row is tagged with its round and every neighbor read verifies the
+    tag.  A clean run raises nothing; a corrupted tag is reported by ``engine.check()``."""
+    c = dict(copy.deepcopy(conf), debug_sequence_check=True)
+    pr = _problem(5, 32, "fused", c, graph=nx.wheel_graph(5))
+    opt = cls(pr, DEV, c)
+    opt.run_rounds(4)
+    torch.cuda.synchronize()
+    eng = opt._program.eng
+    eng.check()
+    assert int(eng.seq_buf.local[opt.k & 1].min()) == opt.k       # rows of the next round to be read are tagged k
+    eng.seq_buf.local[opt.k & 1, 2] = 12345                        # node 2's row now claims a different round
+    opt.run_rounds(1)
+    torch.cuda.synchronize()
+    with pytest.raises(RuntimeError, match="sequence check"):
+        eng.check()
