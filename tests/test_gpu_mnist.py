@@ -261,3 +261,22 @@ def test_sequence_check_passes_and_detects_stale_rows(cls, conf):
     torch.cuda.synchronize()
     with pytest.raises(RuntimeError, match="sequence check"):
         eng.check()
+
+
+@pytest.mark.parametrize("cls,conf", [(DiNNO, DINNO), (DSGD, DSGD_C), (DSGT, dict(DSGT_C, init_grads=False))])
+def test_fused_link_drop_fault_injection_matches_torch_ops(cls, conf):
+    """Time-varying graphs on the fused path: the link drops of ``fault_injection`` become per-round topology tables
+    (several graphs, isolated nodes included) that the kernels index by the device round counter; the PyTorch
+    consensus ops walking the same graph sequence are the oracle."""
+    outs = []
+    for backend in ("fused", "torch"):
+        pr = _problem(6, 32, "fused", conf, graph=nx.cycle_graph(6), eval_every=1000)
+        pr.conf["fault_injection"] = {"link_drop_prob": 0.5, "seed": 3, "from_round": 1, "to_round": 6}
+        pr._init_faults()
+        opt = cls(pr, DEV, dict(copy.deepcopy(conf), consensus_backend="auto" if backend == "fused" else "torch"))
+        opt.train()
+        outs.append(pr.arena.theta.clone())
+        if backend == "fused":
+            assert len(opt._program.eng.topos) > 2            # several distinct faulted graphs were tabulated
+            opt._program.eng.check()
+    _assert_mostly_close(outs[0], outs[1])
