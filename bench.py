@@ -275,7 +275,7 @@ def run_ours(args):
                        "graph": f"cycle, {n_nodes} nodes ({NODES_PER_GPU} per GPU)", "global_batch": BATCH * n_nodes,
                        "primal_iterations": PITS, "seq_len": None, "parallelism": f"consensus graph, {NODES_PER_GPU} nodes/GPU x {args.gpus} GPU",
                        "rounds_per_sec": K / (ms / 1e3), "eval": "excluded from timed region", "kernels": round_kernel,
-                       "l2": f"inputs {NODES_PER_GPU * SAMPLES_PER_NODE * 784 / 1e6:.0f} MB/GPU > L2, random row gather; no flush",
+                       "l2": f"inputs {NODES_PER_GPU * SAMPLES_PER_NODE * 784 / 1e6:.0f} MB/GPU > L2: every round's rows are gathered at random from the HBM-resident shards (never re-used within {SAMPLES_PER_NODE // BATCH} steps); no flush",
                        "input_pipeline": opt_pipeline,
                        "compute": "fp32 CUDA-core fused fwd/bwd + fused consensus kernels (reference runs fp64)",
                        "exchange": f"in-kernel P2P pulls of neighbor rows ({symm_how} peer mapping); no NCCL on the hot path"},
