@@ -13,7 +13,8 @@ from nn_distributed_training_b200.parallel.arena import ROW_ALIGN_ELEMS, SLOT_AL
 from nn_distributed_training_b200.utils import graph_generation
 from nn_distributed_training_b200.utils.graph_generation import Topology
 
-FAST = dict(max_examples=30, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+FAST = dict(max_examples=int(__import__("os").environ.get("HYP_EXAMPLES", "30")), deadline=None, derandomize=True,
+            suppress_health_check=[HealthCheck.too_slow])
 
 
 @settings(**FAST)
