@@ -230,3 +230,21 @@ def test_centralized_baseline(monkeypatch):
     hist = centralized.train_centralized(MNISTConvNet(3, 5, 64), torch.nn.NLLLoss(), tr, va, "cpu", epochs=2, lr=0.005,
                                          batch=50, verbose=False)
     assert hist[-1]["top1_accuracy"] > 0.5 and hist[-1]["validation_loss"] < hist[0]["validation_loss"] * 1.5
+
+
+def test_profile_key_writes_a_profiler_trace(tmp_path, monkeypatch):
+    """``optimizer_config.profile: true``: the runner wraps training in torch.profiler with the
+    reference's schedule and every optimizer calls ``profiler.step()`` once per round -> a trace directory
+    ``<problem_name>opt_profile`` appears in the run's output directory."""
+    import nn_distributed_training_b200.data.mnist as M
+    monkeypatch.setattr(dist_mnist_ex, "load_mnist",
+                        lambda d, train, **k: (M.synthetic_mnist(256 if train else 64, seed=int(train)), "synthetic"))
+    conf = _load("dist_mnist_template.yaml")
+    conf["experiment"].update(output_metadir=str(tmp_path), writeout=True)
+    pc = conf["problem_configs"]["problem1"]
+    pc["optimizer_config"].update(outer_iterations=6, profile=True)      # wait 1 + warmup 1 + active 3 -> one trace
+    pc["metrics_config"]["evaluate_frequency"] = 100
+    dist_mnist_ex.experiment(_write(str(tmp_path), "p.yaml", conf))
+    run = glob.glob(os.path.join(str(tmp_path), "*_dist_mnist_template"))[0]
+    prof_dir = os.path.join(run, pc["problem_name"] + "opt_profile")
+    assert os.path.isdir(prof_dir) and len(os.listdir(prof_dir)) >= 1
