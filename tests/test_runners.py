@@ -248,3 +248,39 @@ def test_profile_key_writes_a_profiler_trace(tmp_path, monkeypatch):
     run = glob.glob(os.path.join(str(tmp_path), "*_dist_mnist_template"))[0]
     prof_dir = os.path.join(run, pc["problem_name"] + "opt_profile")
     assert os.path.isdir(prof_dir) and len(os.listdir(prof_dir)) >= 1
+
+
+def test_fail_fast_guards(tmp_path, synthetic_dir, monkeypatch, capsys):
+    """The reference's runtime guards are kept: hetero split with N > 10, more nodes than waypoint
+    files, NaN in the online forward pass, and the disconnected-graph warning (which does not stop the run)."""
+    import nn_distributed_training_b200.data.mnist as M
+    # hetero split cannot serve more nodes than classes
+    with pytest.raises(NameError, match="Hetero"):
+        dist_mnist_ex.split_hetero(M.synthetic_mnist(200, seed=0), 11)
+    # more robots than waypoint files (4 in the synthetic directory)
+    conf = _small_density_conf("dist_online_dense_PAPER.yaml", synthetic_dir, tmp_path)
+    conf["experiment"]["data"].update(num_scans_in_window=10, num_nodes=9)
+    with pytest.raises(NameError, match="waypoint files"):
+        dist_online_dense_ex.experiment(_write(str(tmp_path), "too_many.yaml", conf))
+    # online problem: tiny comm radius -> warning only; NaN parameters -> fail fast
+    from nn_distributed_training_b200.floorplans.lidar import Lidar2D, OnlineTrajectoryLidarDataset, RandomPoseLidarDataset
+    from nn_distributed_training_b200.models import FourierNet
+    from nn_distributed_training_b200.optimizers import DSGD
+    from nn_distributed_training_b200.problems import DistOnlineDensityProblem
+    lidar = Lidar2D(os.path.join(synthetic_dir, "floor_img.png"), 8, 0.2, 10, 1.0, 20, 3, border_width=8)
+    paths = sorted(glob.glob(os.path.join(synthetic_dir, "tight_paths", "*.npy")))[:3]
+    train = [OnlineTrajectoryLidarDataset(lidar, np.load(p), 4, 10, seed=0, node=i) for i, p in enumerate(paths)]
+    val = RandomPoseLidarDataset(lidar, 10)
+    oc = {"alg_name": "dsgd", "alpha0": 0.01, "mu": 0.0, "outer_iterations": 2, "profile": False}
+    pconf = {"problem_name": "g", "train_batch_size": 100, "val_batch_size": 200, "comm_radius": 1e-3, "dynamic_graph": True,
+             "save_models": False, "metrics": ["validation_loss"], "metrics_config": {"evaluate_frequency": 1, "tloss_decay": 0.2,
+                                                                                     "mesh_only_at_end": True},
+             "optimizer_config": oc}
+    torch.manual_seed(0)
+    pr = DistOnlineDensityProblem(FourierNet([2, 16, 8, 1], 0.05), torch.nn.BCELoss(), train, val, "cpu", pconf)
+    assert "not connected" in capsys.readouterr().out
+    DSGD(pr, "cpu", oc).train()                      # isolated nodes take local steps
+    assert torch.isfinite(pr.arena.theta).all()
+    pr.arena.theta[1].fill_(float("nan"))
+    with pytest.raises(NameError, match="NaN"):
+        pr.local_batch_loss(1)
