@@ -89,3 +89,44 @@ def test_gloo_online_density_runner_matches_single_process(tmp_path):
         assert va.shape == vb.shape and va.shape[1] == 4 and va.shape[0] >= 2
         assert torch.allclose(va, vb, rtol=1e-5, atol=1e-6)
         assert a["forward_pass_count"] == b["forward_pass_count"]
+
+
+def test_gloo_mnist_paper_runner_matches_single_process(tmp_path):
+    """dist_mnist_ex.py + dist_mnist_PAPER.yaml (hetero split, DiNNO / DSGT / DSGD) under torchrun with 2 gloo ranks:
+    rank 0 writes the same files with the same metrics as the single-process run."""
+    import glob
+
+    import yaml
+    with open(os.path.join(ROOT, "experiments", "dist_mnist_PAPER.yaml")) as f:
+        base = yaml.safe_load(f)
+    runner = os.path.join(ROOT, "experiments", "dist_mnist_ex.py")
+    outs = []
+    for tag, nproc in (("single", 1), ("dist", 2)):
+        conf = yaml.safe_load(yaml.safe_dump(base))
+        out = str(tmp_path / tag)
+        os.makedirs(out)
+        e = conf["experiment"]
+        e.update(output_metadir=out, use_cuda=False, data_dir="/nonexistent")      # -> synthetic MNIST
+        e["graph"].update(num_nodes=4)
+        e["individual_training"].update(train_solo=False)
+        for pc in conf["problem_configs"].values():
+            pc["metrics_config"].update(evaluate_frequency=2)
+            pc["optimizer_config"]["outer_iterations"] = 4
+        cfg = os.path.join(out, "m.yaml")
+        with open(cfg, "w") as f:
+            yaml.safe_dump(conf, f)
+        cmd = [sys.executable, runner, cfg] if nproc == 1 else \
+            [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+             "--master-addr", "127.0.0.1", "--master-port", "29614", runner, cfg]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, OMP_NUM_THREADS="2"),
+                           cwd=os.path.join(ROOT, "experiments"))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        outs.append(glob.glob(os.path.join(out, "*_dist_mnist_PAPER"))[0])
+    files = [sorted(f for f in os.listdir(o) if not f.endswith(".yaml")) for o in outs]
+    assert files[0] == files[1] == ["dinno_results.pt", "dsgd_results.pt", "dsgt_results.pt", "graph.gpickle"]
+    for n in files[0][:3]:
+        a = torch.load(os.path.join(outs[0], n), weights_only=False)
+        b = torch.load(os.path.join(outs[1], n), weights_only=False)
+        assert torch.allclose(torch.stack(a["top1_accuracy"]), torch.stack(b["top1_accuracy"]))
+        assert torch.allclose(torch.stack(a["validation_loss"]), torch.stack(b["validation_loss"]), rtol=1e-5, atol=1e-7)
+        assert a["forward_pass_count"] == b["forward_pass_count"]
