@@ -284,3 +284,29 @@ def test_fail_fast_guards(tmp_path, synthetic_dir, monkeypatch, capsys):
     pr.arena.theta[1].fill_(float("nan"))
     with pytest.raises(NameError, match="NaN"):
         pr.local_batch_loss(1)
+
+
+def test_cubi_preproc_writes_the_reference_artefacts(tmp_path):
+    """floorplans/cubi_preproc.py: per-image SDF tensors (negative inside the bright region, height-normalised, zero on
+    the boundary), pzcounts.pt and a 90/10 split_sets.pt — the files the reference's script produces."""
+    from PIL import Image
+    from nn_distributed_training_b200.floorplans import cubi_preproc as cp
+    src, dst = tmp_path / "src", tmp_path / "dst"
+    src.mkdir()
+    for i in range(10):
+        a = np.zeros((80, 120), dtype=np.uint8)
+        a[20 + i: 60, 30: 90 - i] = 255                       # bright rectangle on a dark page
+        Image.fromarray(a, mode="L").save(str(src / f"plan{i}.png"))
+    split = cp.main(["x", str(src), str(dst), "--sidelen", "40", "--seed", "0"])
+    assert len(split["train"]) == 9 and len(split["test"]) == 1
+    assert sorted(split["train"] + split["test"]) == sorted(f"plan{i}.pt" for i in range(10))
+    counts = torch.load(str(dst / "pzcounts.pt"), weights_only=False)
+    sdf = torch.load(str(dst / "plan0.pt"), weights_only=False)
+    assert sdf.shape == (40, 60) and sdf.dtype == torch.float32   # shorter side -> 40, aspect kept
+    assert counts["plan0.pt"] == {"npixels": 2400, "nzeros": int((sdf == 0).sum())} and counts["plan0.pt"]["nzeros"] > 0
+    assert sdf[20, 30] < 0 and sdf[2, 2] > 0                      # inside the rectangle / outside
+    assert abs(float(sdf[2, 2])) <= 1.5 and float(sdf.abs().max()) < 1.5   # normalised by the image height
+    # --no-overwrite keeps existing tensors
+    before = os.path.getmtime(str(dst / "plan3.pt"))
+    cp.main(["x", str(src), str(dst), "--sidelen", "40", "--no-overwrite"])
+    assert os.path.getmtime(str(dst / "plan3.pt")) == before
