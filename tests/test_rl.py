@@ -161,3 +161,27 @@ def test_env_render_and_rollout_gif(tmp_path):
                 out_dir=str(tmp_path), seed=0)
     agent.learn(total_timesteps=20)
     assert any(f.startswith("render_0_") and f.endswith(".gif") for f in os.listdir(str(tmp_path)))
+
+
+def test_reward_and_agreement_plots_read_the_reference_file_names(tmp_path):
+    """RL/plot_reward.py / plot_agreements.py equivalents: centralized ``avg_ep_rews_<ID>.npy``, distributed
+    ``avg_ep_rews_<alg>_<ID>.npy`` (``cadmm`` = DiNNO), mean + min/max band over runs, PNG without matplotlib."""
+    import os
+    from nn_distributed_training_b200.rl import plot_reward as pr
+    d = str(tmp_path)
+    t = np.arange(1, 21) * 100
+    for ID in (1, 2, 3):
+        np.save(os.path.join(d, f"timesteps_{ID}.npy"), t)
+        np.save(os.path.join(d, f"avg_ep_rews_{ID}.npy"), np.linspace(-30, 10 + ID, 20))
+    for alg, ID in (("cadmm", 0), ("dinno", 7), ("dsgt", 13), ("dsgd", 4)):
+        np.save(os.path.join(d, f"timesteps_{alg}_{ID}.npy"), t[:15])
+        np.save(os.path.join(d, f"avg_ep_rews_{alg}_{ID}.npy"), np.linspace(-40, 5 + ID, 15))
+    np.savez(os.path.join(d, "agreements_dsgt_13"), agree_0=np.geomspace(1, 1e-3, 15), agree_1=np.geomspace(1, 2e-3, 15),
+             agree_2=np.geomspace(1, 3e-3, 15))
+    s = pr.summarize(d)
+    assert s["centralized"]["runs"] == 3 and s["dinno"]["runs"] == 2 and s["dsgt"]["runs"] == 1 and s["dsgd"]["runs"] == 1
+    assert abs(s["centralized"]["final_mean"] - 12.0) < 1e-9
+    out = pr.plot(d, out=os.path.join(d, "RL_reward.png"))
+    assert os.path.getsize(out) > 500
+    out = pr.plot_agreements(os.path.join(d, "agreements_dsgt_13.npz"), out=os.path.join(d, "RL_agreement.png"))
+    assert os.path.getsize(out) > 500
