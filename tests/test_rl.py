@@ -185,3 +185,18 @@ def test_reward_and_agreement_plots_read_the_reference_file_names(tmp_path):
     assert os.path.getsize(out) > 500
     out = pr.plot_agreements(os.path.join(d, "agreements_dsgt_13.npz"), out=os.path.join(d, "RL_agreement.png"))
     assert os.path.getsize(out) > 500
+
+
+def test_train_script_cli_writes_the_artefacts(tmp_path):
+    """`python -m nn_distributed_training_b200.rl.train_dsgd_multi ...` (reference: RL/dist_rl/train_dsgd_multi.py):
+    one iteration, files named as the reference names them, episode GIF when --render."""
+    import os
+    from nn_distributed_training_b200.rl import plot_reward, train_dsgd_multi
+    out = str(tmp_path / "trained")
+    train_dsgd_multi.main(["--max_rl_timesteps", "1500", "--num_envs", "4", "--out_dir", out, "--save_freq", "1",
+                           "--render", "--render_every_i", "1", "--seed", "0", "--ID", "3"])
+    files = set(os.listdir(out))
+    assert {"ppo_actors_tag_dsgd_3_0.pth", "ppo_critics_tag_dsgd_3_0.pth", "avg_ep_rews_dsgd_3.npy", "timesteps_dsgd_3.npy",
+            "agreements_dsgd_3.npz", "dsgd_3_0.gif"} <= files
+    s = plot_reward.summarize(out)
+    assert s["dsgd"]["runs"] == 1
