@@ -11,4 +11,8 @@ def get_args(argv=None):
     p.add_argument("--total_timesteps", type=int, default=10_000_000)
     p.add_argument("--device", type=str, default="cpu")
     p.add_argument("--render", type=str, default="")          # test mode: write a GIF of the first episode here
+    p.add_argument("--out_dir", type=str, default="./trained")  # train mode: weights + reward curves
+    p.add_argument("--ID", type=int, default=0)
+    p.add_argument("--save_freq", type=int, default=10)
+    p.add_argument("--seed", type=int, default=None)
     return p.parse_args(argv)

@@ -45,7 +45,8 @@ def test(env, actor_model, render_to=None):
 def main(argv=None):
     args = get_args(argv)
     hyper = {"timesteps_per_batch": 2000, "max_timesteps_per_episode": 200, "gamma": 0.99,
-             "n_updates_per_iteration": 10, "lr": 3e-4, "clip": 0.2}
+             "n_updates_per_iteration": 10, "lr": 3e-4, "clip": 0.2, "out_dir": args.out_dir, "ID": args.ID,
+             "save_freq": args.save_freq, "seed": args.seed}
     env = make_env(args.num_envs, 200, args.device)
     if args.mode == "train":
         train(env, hyper, args.actor_model, args.critic_model, args.total_timesteps)
