@@ -81,8 +81,9 @@ def plot_run(run_dir: str, out: str, evaluate_frequency: int = 20):
         matplotlib.use("Agg")
         import matplotlib.pyplot as plt
     except ImportError:
-        print("matplotlib is not installed: printing the text summary instead")
-        return summarize_run(run_dir)
+        from .figures import curves_figure          # same three panels drawn with PIL
+        summarize_run(run_dir)
+        return curves_figure(run_dir, out[:-4] + ".png" if out.endswith(".svg") else out, evaluate_frequency)
     res = load_results(run_dir)
     fig, axes = plt.subplots(1, 3, figsize=(14, 4))
     for name, m in res.items():

@@ -142,6 +142,22 @@ def test_online_density_runner_dynamic_graph(tmp_path, synthetic_dir):
     assert len(frames) == 1 and frames[0].size[0] > 10
     gif = animations.save_gif(frames * 2, os.path.join(str(tmp_path), "d.gif"))
     assert os.path.getsize(gif) > 100
+    # static figures of the notebooks without matplotlib: curves, density panel next to the ground truth, lidar figure
+    from nn_distributed_training_b200.floorplans.lidar import Lidar2D, OnlineTrajectoryLidarDataset
+    from nn_distributed_training_b200.visualization import figures, load_results
+    assert os.path.getsize(figures.curves_figure(out, os.path.join(str(tmp_path), "curves.png"), 3)) > 500
+    lidar = Lidar2D(os.path.join(synthetic_dir, "floor_img.png"), 8, 0.2, 10, 1.0, 20, 3, border_width=8)
+    allres = load_results(out)
+    panel = figures.density_panel(allres, os.path.join(str(tmp_path), "panel.png"), lidar=lidar, node=0)
+    from PIL import Image
+    assert Image.open(panel).size[0] > Image.open(panel).size[1]          # ground truth + 3 algorithms side by side
+    paths = sorted(glob.glob(os.path.join(synthetic_dir, "tight_paths", "*.npy")))[:2]
+    dsets = [OnlineTrajectoryLidarDataset(lidar, np.load(p), 4, 10, seed=0, node=i) for i, p in enumerate(paths)]
+    fig = figures.lidar_figure(lidar, dsets, os.path.join(str(tmp_path), "lidar.png"))
+    cols = {c for _, c in Image.open(fig).getcolors(maxcolors=1 << 20)}
+    assert (255, 215, 0) in cols and (0, 0, 139) in cols                 # occupied (gold) and free (dark blue) samples drawn
+    assert os.path.getsize(figures.compare_runs_figure([out, out], os.path.join(str(tmp_path), "cmp.png"), 3,
+                                                       key="validation_loss")) > 500
 
 
 def test_offline_density_runner(tmp_path, synthetic_dir):
