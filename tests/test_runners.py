@@ -326,3 +326,21 @@ def test_cubi_preproc_writes_the_reference_artefacts(tmp_path):
     before = os.path.getmtime(str(dst / "plan3.pt"))
     cp.main(["x", str(src), str(dst), "--sidelen", "40", "--no-overwrite"])
     assert os.path.getmtime(str(dst / "plan3.pt")) == before
+
+
+def test_centralized_baselines(tmp_path, synthetic_dir, monkeypatch):
+    """centralized/*.ipynb equivalents: one model on the union of every node's data, for the MNIST and the lidar-density
+    configs (the dotted "Centralized" reference lines of the figures)."""
+    import nn_distributed_training_b200.data.mnist as M
+    from nn_distributed_training_b200.experiments import centralized
+    monkeypatch.setattr(centralized, "load_mnist",
+                        lambda d, train, **k: (M.synthetic_mnist(600 if train else 200, seed=int(train)), "synthetic"))
+    conf = _load("dist_mnist_template.yaml")
+    conf["experiment"].update(output_metadir=str(tmp_path), use_cuda=False)
+    conf["experiment"]["individual_training"].update(epochs=2, lr=0.005, train_batch_size=50, val_batch_size=100)
+    hist = centralized.centralized_mnist(_write(str(tmp_path), "cm.yaml", conf))
+    assert len(hist) == 2 and hist[-1]["top1_accuracy"] > hist[0]["top1_accuracy"] - 1e-9 and hist[-1]["top1_accuracy"] > 0.3
+    dconf = _small_density_conf("dist_online_dense_PAPER.yaml", synthetic_dir, tmp_path)
+    dconf["experiment"]["individual_training"].update(epochs=1)
+    hist = centralized.centralized_density(_write(str(tmp_path), "cd.yaml", dconf), online=True)
+    assert len(hist) == 1 and np.isfinite(hist[0]["validation_loss"]) and hist[0]["top1_accuracy"] is None
