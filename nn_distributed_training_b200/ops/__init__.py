@@ -38,10 +38,25 @@ def fused_available() -> bool:
     return True
 
 
-def mnist_kernel_supports(spec, batch_size: int) -> bool:
-    """Shapes the hand-written MNIST kernel is instantiated for."""
+def mnist_kernel_is_paper_shape(spec) -> bool:
+    """The specialised kernels (mnist.cu / mnist_tc.cu) are written for the paper's MNISTConvNet(3, 5, 64)."""
     return (spec.in_hw == 28 and spec.num_classes == 10 and spec.kernel_size == 5
-            and spec.num_filters == 3 and spec.linear_width == 64 and 1 <= batch_size <= 4096)
+            and spec.num_filters == 3 and spec.linear_width == 64)
+
+
+def mnist_kernel_supports(spec, batch_size: int, dtype=None) -> bool:
+    """Conv-net shapes / dtypes with a hand-written forward+backward kernel: the paper shape in fp32 (specialised
+    kernels) and, through csrc/mnist_generic.cu, num_filters <= 8, kernel_size in {3, 5}, linear_width <= 128 in fp32 or
+    fp64."""
+    import torch
+
+    if not (spec.in_hw == 28 and spec.num_classes == 10 and 1 <= batch_size <= 4096):
+        return False
+    if dtype not in (None, torch.float32, torch.float64):
+        return False
+    if dtype in (None, torch.float32) and mnist_kernel_is_paper_shape(spec):
+        return True
+    return 1 <= spec.num_filters <= 8 and spec.kernel_size in (3, 5) and 1 <= spec.linear_width <= 128
 
 
 def mlp_kernel_supports(spec, base_loss) -> bool:

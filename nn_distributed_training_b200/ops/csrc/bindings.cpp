@@ -27,7 +27,8 @@ static double getf(const py::dict& d, const char* k, double dflt = 0) { return d
 // ------------------------------------------------------------------ MNIST ----
 struct MnistOp {
   mnist::Args a{};
-  int spb = 8, S = 1, eval_ctas = 1;
+  mnist::GenericShape gs{3, 5, 64, 0};
+  int spb = 8, S = 1, eval_ctas = 1, generic = 0;
   explicit MnistOp(const py::dict& d) { update(d); }
   void update(const py::dict& d) {
     a.theta = ptr<const float>(d, "theta"); a.n_pad = geti(d, "n_pad"); a.L = geti(d, "L");
@@ -42,9 +43,19 @@ struct MnistOp {
     a.n_val = geti(d, "n_val"); a.val_loss = ptr<float>(d, "val_loss");
     a.val_correct = ptr<unsigned char>(d, "val_correct");
     spb = geti(d, "spb", 8); S = geti(d, "S", 1); eval_ctas = geti(d, "eval_ctas", 1);
+    // generic CUDA-core kernel (mnist_generic.cu): any conv shape, fp32 / fp64 (theta, grad_part, val_loss then address doubles)
+    generic = geti(d, "generic", 0);
+    gs.F = geti(d, "num_filters", 3); gs.KS = geti(d, "kernel_size", 5); gs.LW = geti(d, "linear_width", 64);
+    gs.dtype64 = geti(d, "dtype64", 0);
   }
-  void train() { check(mnist::launch_train(a, spb, S, cur_stream()), "mnist_train"); }
-  void eval() { check(mnist::launch_eval(a, eval_ctas, cur_stream()), "mnist_eval"); }
+  void train() {
+    if (generic) check(mnist::launch_generic_train(a, gs, spb, S, cur_stream()), "convnet_generic_train");
+    else check(mnist::launch_train(a, spb, S, cur_stream()), "mnist_train");
+  }
+  void eval() {
+    if (generic) check(mnist::launch_generic_eval(a, gs, eval_ctas, cur_stream()), "convnet_generic_eval");
+    else check(mnist::launch_eval(a, eval_ctas, cur_stream()), "mnist_eval");
+  }
 };
 
 struct GatherOp {
@@ -81,6 +92,9 @@ static consensus::Common<T> common_from(const py::dict& d) {
   c.world = geti(d, "world", 1); c.rank = geti(d, "rank", 0);
   c.done_ctr = ptr<unsigned int>(d, "done_ctr"); c.err = ptr<int>(d, "err");
   c.flags_in_kernel = geti(d, "flags_in_kernel", 1);
+  c.flag_pull = geti(d, "flag_pull", 0); c.peer_pub = ptr<const int64_t>(d, "peer_pub");
+  c.notify_mask = d.contains("notify_mask") ? d["notify_mask"].cast<unsigned long long>() : ~0ull;
+  c.node_order = ptr<const int>(d, "node_order");
   c.pub_seq = ptr<int>(d, "pub_seq"); c.nbr_seq = ptr<const int64_t>(d, "nbr_seq");
   c.sum_mode = geti(d, "sum_mode", 0); c.n_total = geti(d, "n_total", 0);
   c.sum_local = ptr<double>(d, "sum_local"); c.sum_mc = ptr<const double>(d, "sum_mc");
@@ -168,6 +182,15 @@ PYBIND11_MODULE(_C, m) {
     check(f64 ? consensus::launch_consensus_metric<double>(r, N, n_pad, local0, L, a, b, c, cur_stream())
               : consensus::launch_consensus_metric<float>(r, N, n_pad, local0, L, a, b, c, cur_stream()), "consensus_metric");
   });
+  m.def("convnet_generic_smem_bytes", [](int F, int KS, int LW, int dtype64, int spb) {
+    return (size_t)mnist::generic_smem_bytes(mnist::GenericShape{F, KS, LW, dtype64}, dtype64, spb);
+  });
+  m.def("rank_barrier", [](uint64_t slots, uint64_t peer_slot, int world, int rank, int epoch, uint64_t gate, uint64_t err) {
+    check(consensus::launch_rank_barrier(reinterpret_cast<int*>(slots), reinterpret_cast<const int64_t*>(peer_slot), world, rank,
+                                         epoch, reinterpret_cast<const volatile int*>(gate), reinterpret_cast<int*>(err), cur_stream()),
+          "rank_barrier");
+  });
+  m.def("spin", [](long long cycles) { check(consensus::launch_spin(cycles, cur_stream()), "spin"); });
   py::class_<DinnoRoundOp>(m, "DinnoRoundOp")
       .def(py::init<const py::dict&, const py::dict&, const py::list&>())
       .def("launch", &DinnoRoundOp::launch);

@@ -67,9 +67,7 @@ __global__ void __launch_bounds__(THREADS) local_sum_kernel(const Common<T> c) {
 template <typename T>
 __global__ void publish_round_kernel(const Common<T> c) {
   const int k = *reinterpret_cast<volatile int*>(c.round_ctr);
-  __threadfence_system();
-  if ((int)threadIdx.x < c.world && (int)threadIdx.x != c.rank)
-    st_release_sys(reinterpret_cast<int*>(c.peer_flag[threadIdx.x]), k);
+  announce_round(c, k);
 }
 
 // ------------------------------------------------------------------ DiNNO ----
@@ -77,7 +75,7 @@ template <typename T>
 __global__ void __launch_bounds__(THREADS) dinno_update_kernel(const DinnoArgs<T> a) {
   const Common<T>& c = a.c;
   constexpr int N = Vec<T>::N;
-  const int l = blockIdx.y;
+  const int l = node_of_block(c);
   const RoundInfo<T> ri = round_info(c);
   const int deg = c.deg[ri.gid * c.L + l];
   const DinnoCoef<T> cf = dinno_coef(a, ri.k, a.step, deg);
@@ -105,10 +103,18 @@ __global__ void __launch_bounds__(THREADS) dinno_update_kernel(const DinnoArgs<T
 #pragma unroll
         for (int u = 0; u < N; ++u) dl.v[u] = (T)(sall.v[u] - (double)c.n_total * (double)thk.v[u]);
       } else {
-        for (int e = 0; e < deg; ++e) {
-          const Pack<T> q = ldv(nbr_row(c, ri.gid, l, e, ri.par, 0) + i);
+        // up to four neighbor rows in flight per thread: over NVLink a load is ~2 us, issued one by one they add up
+        for (int e0 = 0; e0 < deg; e0 += 4) {
+          Pack<T> q[4];
 #pragma unroll
-          for (int u = 0; u < N; ++u) dl.v[u] += q.v[u] - thk.v[u];
+          for (int j = 0; j < 4; ++j)
+            if (e0 + j < deg) q[j] = ldv(nbr_row(c, ri.gid, l, e0 + j, ri.par, 0) + i);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (e0 + j < deg) {
+#pragma unroll
+              for (int u = 0; u < N; ++u) dl.v[u] += q[j].v[u] - thk.v[u];
+            }
         }
       }
       du = ldv(a.dual + row + i);
@@ -152,7 +158,7 @@ __global__ void __launch_bounds__(THREADS) dsgd_mix_kernel(const Common<T> c) {
   pdl_wait();
   pdl_launch_dependents();
   constexpr int N = Vec<T>::N;
-  const int l = blockIdx.y;
+  const int l = node_of_block(c);
   const RoundInfo<T> ri = round_info(c);
   const int deg = c.deg[ri.gid * c.L + l];
   if (c.sum_mode) wait_all_sums(c, ri.k); else wait_neighbors(c, ri.gid, l, ri.k);
@@ -171,11 +177,18 @@ __global__ void __launch_bounds__(THREADS) dsgd_mix_kernel(const Common<T> c) {
     Pack<T> th = ldv(c.theta + row + i);
 #pragma unroll
     for (int u = 0; u < N; ++u) th.v[u] *= ws;
-    for (int e = 0; e < deg; ++e) {
-      const Pack<T> q = ldv(nbr_row(c, ri.gid, l, e, ri.par, 0) + i);
-      const T we = w[e];
+    for (int e0 = 0; e0 < deg; e0 += 4) {
+      Pack<T> q[4];
 #pragma unroll
-      for (int u = 0; u < N; ++u) th.v[u] += we * q.v[u];
+      for (int j = 0; j < 4; ++j)
+        if (e0 + j < deg) q[j] = ldv(nbr_row(c, ri.gid, l, e0 + j, ri.par, 0) + i);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (e0 + j < deg) {
+          const T we = w[e0 + j];
+#pragma unroll
+          for (int u = 0; u < N; ++u) th.v[u] += we * q[j].v[u];
+        }
     }
     stv(c.theta + row + i, th);
   }
@@ -186,7 +199,7 @@ __global__ void __launch_bounds__(THREADS) dsgd_step_kernel(const Common<T> c) {
   pdl_wait();
   pdl_launch_dependents();
   constexpr int N = Vec<T>::N;
-  const int l = blockIdx.y;
+  const int l = node_of_block(c);
   const RoundInfo<T> ri = round_info(c);
   const T alpha = c.alpha[ri.k];
   const size_t row = (size_t)l * c.n_pad;
@@ -211,7 +224,7 @@ __global__ void __launch_bounds__(THREADS) dsgt_init_kernel(const DsgtArgs<T> a)
   pdl_launch_dependents();
   const Common<T>& c = a.c;
   constexpr int N = Vec<T>::N;
-  const int l = blockIdx.y;
+  const int l = node_of_block(c);
   const size_t row = (size_t)l * c.n_pad;
   for (int i = (blockIdx.x * THREADS + threadIdx.x) * N; i < c.n_pad; i += gridDim.x * THREADS * N) {
     const Pack<T> g = sum_partials(c, l, i);
@@ -227,7 +240,7 @@ __global__ void __launch_bounds__(THREADS) dsgt_mix_kernel(const DsgtArgs<T> a) 
   pdl_launch_dependents();
   const Common<T>& c = a.c;
   constexpr int N = Vec<T>::N;
-  const int l = blockIdx.y;
+  const int l = node_of_block(c);
   const RoundInfo<T> ri = round_info(c);
   const int deg = c.deg[ri.gid * c.L + l];
   if (c.sum_mode) wait_all_sums(c, ri.k); else wait_neighbors(c, ri.gid, l, ri.k);
@@ -249,12 +262,21 @@ __global__ void __launch_bounds__(THREADS) dsgt_mix_kernel(const DsgtArgs<T> a) 
     const Pack<T> y = ldv(ys + i);
 #pragma unroll
     for (int u = 0; u < N; ++u) th.v[u] = ws * (th.v[u] - alpha * y.v[u]);
-    for (int e = 0; e < deg; ++e) {
-      const Pack<T> qt = ldv(nbr_row(c, ri.gid, l, e, ri.par, 0) + i);
-      const Pack<T> qy = ldv(nbr_row(c, ri.gid, l, e, ri.par, 1) + i);
-      const T we = w[e];
+    for (int e0 = 0; e0 < deg; e0 += 2) {
+      Pack<T> qt[2], qy[2];
 #pragma unroll
-      for (int u = 0; u < N; ++u) th.v[u] += we * (qt.v[u] - alpha * qy.v[u]);
+      for (int j = 0; j < 2; ++j)
+        if (e0 + j < deg) {
+          qt[j] = ldv(nbr_row(c, ri.gid, l, e0 + j, ri.par, 0) + i);
+          qy[j] = ldv(nbr_row(c, ri.gid, l, e0 + j, ri.par, 1) + i);
+        }
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        if (e0 + j < deg) {
+          const T we = w[e0 + j];
+#pragma unroll
+          for (int u = 0; u < N; ++u) th.v[u] += we * (qt[j].v[u] - alpha * qy[j].v[u]);
+        }
     }
     stv(c.theta + row + i, th);
   }
@@ -266,7 +288,7 @@ __global__ void __launch_bounds__(THREADS) dsgt_track_kernel(const DsgtArgs<T> a
   pdl_launch_dependents();
   const Common<T>& c = a.c;
   constexpr int N = Vec<T>::N;
-  const int l = blockIdx.y;
+  const int l = node_of_block(c);
   const RoundInfo<T> ri = round_info(c);
   const int deg = c.deg[ri.gid * c.L + l];
   const T ws = c.self_w[ri.gid * c.L + l];
@@ -283,11 +305,18 @@ __global__ void __launch_bounds__(THREADS) dsgt_track_kernel(const DsgtArgs<T> a
       y = ldv(ys + i);
 #pragma unroll
       for (int u = 0; u < N; ++u) y.v[u] *= ws;
-      for (int e = 0; e < deg; ++e) {
-        const Pack<T> qy = ldv(nbr_row(c, ri.gid, l, e, ri.par, 1) + i);
-        const T we = w[e];
+      for (int e0 = 0; e0 < deg; e0 += 4) {
+        Pack<T> q[4];
 #pragma unroll
-        for (int u = 0; u < N; ++u) y.v[u] += we * qy.v[u];
+        for (int j = 0; j < 4; ++j)
+          if (e0 + j < deg) q[j] = ldv(nbr_row(c, ri.gid, l, e0 + j, ri.par, 1) + i);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (e0 + j < deg) {
+            const T we = w[e0 + j];
+#pragma unroll
+            for (int u = 0; u < N; ++u) y.v[u] += we * q[j].v[u];
+          }
       }
     }
     const Pack<T> gn = sum_partials(c, l, i);
@@ -355,6 +384,40 @@ cudaError_t launch_consensus_metric(const int64_t* rows, int N, int n_pad, int l
                                     double* out_pair, double* out_mean, cudaStream_t st) {
   inv_norm_kernel<T><<<N, THREADS, 0, st>>>(rows, n_pad, inv_norm);
   consensus_metric_kernel<T><<<dim3(N + 1, L), THREADS, 0, st>>>(rows, N, n_pad, local0, inv_norm, out_pair, out_mean);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------ rank barrier ----
+__global__ void rank_barrier_kernel(int* slots, const int64_t* peer_slot, int world, int rank, int epoch,
+                                    const volatile int* gate, int* err) {
+  if (gate != nullptr && threadIdx.x == 0) {
+    const long long t0 = clock64();
+    while (*gate == 0) {
+      if (clock64() - t0 > kSpinLimit) { if (err) *err = 1; break; }
+    }
+  }
+  __syncthreads();
+  const int r = threadIdx.x;
+  if (r < world && r != rank) {
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<int*>(peer_slot[r]), epoch);
+    const long long t0 = clock64();
+    while (ld_acquire_sys(slots + r) < epoch) {
+      if (clock64() - t0 > kSpinLimit) { if (err) *err = 1; break; }
+    }
+  }
+}
+cudaError_t launch_rank_barrier(int* slots, const int64_t* peer_slot, int world, int rank, int epoch,
+                                const volatile int* gate, int* err, cudaStream_t st) {
+  rank_barrier_kernel<<<1, 64, 0, st>>>(slots, peer_slot, world, rank, epoch, gate, err);
+  return cudaGetLastError();
+}
+__global__ void spin_kernel(long long cycles) {
+  const long long t0 = clock64();
+  while (clock64() - t0 < cycles) {}
+}
+cudaError_t launch_spin(long long cycles, cudaStream_t st) {
+  spin_kernel<<<1, 1, 0, st>>>(cycles);
   return cudaGetLastError();
 }
 

@@ -45,6 +45,13 @@ struct Common {
   int* flags;                 // [world] local slots written by peers (round published)
   const int64_t* peer_flag;   // [world] address of *their* slot for this rank
   int world, rank;
+  // flag transport: push (default) = the producer stores k+1 into the reader's local slot over NVLink and readers spin on
+  // local memory; pull = the producer only releases its own counter (slot `rank` of its own array, no remote store on its
+  // critical path) and readers poll that slot over NVLink through `peer_pub`.
+  int flag_pull;
+  const int64_t* peer_pub;    // [world] address of rank r's own counter (pull mode)
+  unsigned long long notify_mask;  // ranks that ever own a neighbor of a local node: the only ones told about a new round
+  const int* node_order;      // [L] launch order of the local nodes (nodes with remote neighbors first), nullptr = identity
   unsigned int* done_ctr;     // [1] last-block detection
   int* err;                   // [1] 1 = spin timeout, 2 = sequence check failed
   // optional debug build of the protocol: every published row carries the round it belongs to and every
@@ -85,6 +92,14 @@ template <typename T> cudaError_t launch_dsgt_mix(const DsgtArgs<T>& a, cudaStre
 template <typename T> cudaError_t launch_dsgt_track(const DsgtArgs<T>& a, cudaStream_t st);
 template <typename T> cudaError_t launch_local_sum(const Common<T>& c, cudaStream_t st);
 template <typename T> cudaError_t launch_publish_round(const Common<T>& c, cudaStream_t st);
+
+// All-rank barrier on the device (bench start alignment, metric quiescence): every rank stores `epoch` into its slot of
+// every peer's array and spins until all of its own slots reached it; with `gate` != nullptr the kernel first spins on that
+// (pinned host) word until the host sets it, so everything enqueued behind it starts at the host's command.
+cudaError_t launch_rank_barrier(int* slots, const int64_t* peer_slot, int world, int rank, int epoch,
+                                const volatile int* gate, int* err, cudaStream_t st);
+// Busy-wait `cycles` SM clocks (tests: a deliberately delayed rank)
+cudaError_t launch_spin(long long cycles, cudaStream_t st);
 
 // K6 consensus metric (problems/dist_mnist_problem.py:155-169): distances between L2-normalised parameter rows.
 // rows[j] is the device address of node j's current row (local, or a peer GPU's published row over NVLink).

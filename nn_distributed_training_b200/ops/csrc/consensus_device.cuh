@@ -38,8 +38,32 @@ NNDT_DEVINL RoundInfo<T> round_info(const Common<T>& c) {
   return r;
 }
 
-// wait until every rank owning a neighbor of local node l has published round k; with the sequence check enabled,
-// also verify that the row about to be read is tagged with round k
+// local node handled by this CTA row: nodes whose neighbors live on other GPUs are launched first, so their NVLink
+// pulls run in the shadow of the preceding forward/backward kernel (the update grid only becomes fully resident when
+// that kernel drains)
+template <typename T>
+NNDT_DEVINL int node_of_block(const Common<T>& c) {
+  return c.node_order != nullptr ? c.node_order[blockIdx.y] : (int)blockIdx.y;
+}
+
+// spin until rank r has published round k (push: peers store into our local slot; pull: poll r's own counter over NVLink)
+template <typename T>
+NNDT_DEVINL void wait_rank(const Common<T>& c, int r, int k) {
+  const int* f = c.flag_pull ? reinterpret_cast<const int*>(c.peer_pub[r]) : c.flags + r;
+  if (ld_acquire_sys(f) >= k) return;
+  if (*reinterpret_cast<volatile int*>(c.err) != 0) return;      // a peer already timed out: do not stack 10 s spins
+  const long long t0 = clock64();
+  while (ld_acquire_sys(f) < k) {
+    if (clock64() - t0 > kSpinLimit) { *c.err = 1; break; }
+  }
+}
+
+// Wait until every rank owning a neighbor of local node l has published round k; with the sequence check enabled,
+// also verify that the row about to be read is tagged with round k.
+// Buffer reuse on time-varying graphs: this node overwrites pub[(k+1)&1] at the end of round k, the buffer its
+// round-(k-1) neighbors read during round k-1.  A rank publishes round k only after its round-(k-1) reads, so also
+// waiting for "round k published" from the ranks of the round-(k-1) neighbors (a no-op on static graphs: same set)
+// closes the write-after-read window without a separate "consumed" counter.
 template <typename T>
 NNDT_DEVINL void wait_neighbors(const Common<T>& c, int gid, int l, int k) {
   const bool check = c.nbr_seq != nullptr;
@@ -47,15 +71,20 @@ NNDT_DEVINL void wait_neighbors(const Common<T>& c, int gid, int l, int k) {
     const int d = c.deg[gid * c.L + l];
     if ((int)threadIdx.x < d) {
       const int r = c.world > 1 ? c.nbr_rank[(gid * c.L + l) * c.dmax + threadIdx.x] : -1;
-      if (r >= 0) {
-        const long long t0 = clock64();
-        while (ld_acquire_sys(c.flags + r) < k) {
-          if (clock64() - t0 > kSpinLimit) { *c.err = 1; break; }
-        }
-      }
+      if (r >= 0) wait_rank(c, r, k);
       if (check) {
         const int* tag = reinterpret_cast<const int*>(c.nbr_seq[((size_t)(gid * c.L + l) * c.dmax + threadIdx.x) * 2 + (k & 1)]);
         if (ld_acquire_sys(tag) != k) *c.err = 2;
+      }
+    }
+    if (c.world > 1 && k > 0) {
+      const int gp = c.graph_id[k - 1];
+      if (gp != gid) {
+        const int t = (int)threadIdx.x - 32;                  // a different warp than the current-graph waiters
+        if (t >= 0 && t < c.deg[gp * c.L + l]) {
+          const int r = c.nbr_rank[(gp * c.L + l) * c.dmax + t];
+          if (r >= 0) wait_rank(c, r, k);
+        }
       }
     }
     __syncthreads();
@@ -66,6 +95,20 @@ NNDT_DEVINL void wait_neighbors(const Common<T>& c, int gid, int l, int k) {
 template <typename T>
 NNDT_DEVINL void tag_published(const Common<T>& c, int l, int k) {
   if (c.pub_seq != nullptr && blockIdx.x == 0 && threadIdx.x == 0) c.pub_seq[((k + 1) & 1) * c.pub_L + l] = k + 1;
+}
+
+// tell the peers that every round below `kn` is published (called by threads 0..world-1 of ONE block after the rows are
+// ordered before this point at gpu scope).  push: one remote store per rank that ever owns a neighbor; pull: a single
+// release of this rank's own counter — nothing crosses NVLink on the producer's critical path.
+template <typename T>
+NNDT_DEVINL void announce_round(const Common<T>& c, int kn) {
+  if (c.flag_pull) {
+    if (threadIdx.x == 0) { __threadfence_system(); st_release_sys(c.flags + c.rank, kn); }
+  } else {
+    __threadfence_system();
+    if ((int)threadIdx.x < c.world && (int)threadIdx.x != c.rank && ((c.notify_mask >> threadIdx.x) & 1ull))
+      st_release_sys(reinterpret_cast<int*>(c.peer_flag[threadIdx.x]), kn);
+  }
 }
 
 // last block of the launch: advance the round counter and announce the new round to peers
@@ -89,11 +132,7 @@ NNDT_DEVINL void finish_round(const Common<T>& c, int k) {
       *c.done_ctr = 0;
       *c.round_ctr = k + 1;
     }
-    if (announce) {
-      __threadfence_system();
-      if ((int)threadIdx.x < c.world && (int)threadIdx.x != c.rank)
-        st_release_sys(reinterpret_cast<int*>(c.peer_flag[threadIdx.x]), k + 1);
-    }
+    if (announce) announce_round(c, k + 1);
   }
 }
 

@@ -52,6 +52,12 @@ struct GatherArgs {
   unsigned int* done_ctr;        // [1]
   int max_blocks;                // grid cap: the staging blocks must leave one SM per concurrent training CTA
 };
+// Generic CUDA-core conv net (mnist_generic.cu): any (num_filters <= 8, kernel_size in {3,5}, linear_width <= 128), fp32 or
+// fp64.  With dtype64 the Args pointers theta / grad_part / val_loss address doubles (loss_part stays float).
+struct GenericShape { int F, KS, LW, dtype64; };
+size_t generic_smem_bytes(const GenericShape& gs, int dtype64, int spb);
+cudaError_t launch_generic_train(const Args& a, const GenericShape& gs, int spb, int S, cudaStream_t st);
+cudaError_t launch_generic_eval(const Args& a, const GenericShape& gs, int ctas_per_node, cudaStream_t st);
 cudaError_t launch_gather(const GatherArgs& a, cudaStream_t st);
 cudaError_t launch_train(const Args& a, int spb, int S, cudaStream_t st);
 cudaError_t launch_eval(const Args& a, int ctas_per_node, cudaStream_t st);

@@ -121,6 +121,26 @@ class ConsensusEngine:
         for r in range(ctx.world_size):
             peer_flag[r] = self.flag_buf.peer_ptrs[r] + 4 * ctx.rank
         self.t_peer_flag = torch.as_tensor(peer_flag, device=dev)
+        # pull transport: rank r's own counter is slot r of its own array; readers poll it over NVLink
+        peer_pub = np.zeros(max(ctx.world_size, 1), dtype=np.int64)
+        for r in range(ctx.world_size):
+            peer_pub[r] = self.flag_buf.peer_ptrs[r] + 4 * r
+        self.t_peer_pub = torch.as_tensor(peer_pub, device=dev)
+        self.flag_mode = os.environ.get("NNDT_FLAG_MODE", str(opt.conf.get("flag_transport", pr.conf.get("flag_transport", "push"))))
+        if self.flag_mode not in ("push", "pull"):
+            raise ValueError(f"flag_transport must be push or pull, got {self.flag_mode!r}")
+        # ranks that own a neighbor of a local node in ANY round's graph: the only ones that need this rank's flags
+        notify = 0
+        remote_node = np.zeros(L, dtype=bool)
+        for r in np.unique(nbr_rank[nbr_rank >= 0]):
+            notify |= 1 << int(r)
+        for l in range(L):
+            remote_node[l] = bool((nbr_rank[:, l, :] >= 0).any())
+        self.notify_mask = notify
+        # launch order of the local nodes: the ones pulling over NVLink first (their CTAs become resident while the
+        # preceding forward/backward kernel still runs, which hides the link latency)
+        order = np.argsort(~remote_node, kind="stable").astype(np.int32)
+        self.t_node_order = torch.as_tensor(order, device=dev)
         if ctx.is_distributed:
             torch.cuda.synchronize(dev)
             ctx.barrier()
@@ -163,7 +183,10 @@ class ConsensusEngine:
                  rho=self.rho.data_ptr(), lr=self.lr.data_ptr(), alpha=self.alpha.data_ptr(),
                  graph_id=self.t_gid.data_ptr(), calls=None if calls is None else calls.data_ptr(),
                  flags=self.flag_buf.local.data_ptr(), peer_flag=self.t_peer_flag.data_ptr(),
-                 world=ctx.world_size, rank=ctx.rank, done_ctr=self.done_ctr.data_ptr(), err=self.err.data_ptr())
+                 world=ctx.world_size, rank=ctx.rank, done_ctr=self.done_ctr.data_ptr(), err=self.err.data_ptr(),
+                 flag_pull=int(self.flag_mode == "pull"), peer_pub=self.t_peer_pub.data_ptr(),
+                 notify_mask=int(self.notify_mask) if ctx.world_size > 1 else 0,
+                 node_order=self.t_node_order.data_ptr() if ctx.world_size > 1 else None)
         # the C++ side indexes pub rows with stride L; when ranks host different node counts the
         # published buffer is allocated with the max count, so pass that as the row count of pub
         d["L"] = L

@@ -11,7 +11,7 @@ import os
 import numpy as np
 import torch
 
-from . import load_ext
+from . import load_ext, mnist_kernel_is_paper_shape
 
 SPB = 8  # samples per CTA of the evaluation kernel / upper bound for training (template instantiations in mnist.cu)
 
@@ -35,9 +35,21 @@ class FusedMnist:
         self.L, self.n_pad = pl.L, a.n_pad
         self.B = problem.train_batch_size
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        self.spb = (int(os.environ.get("NNDT_SPB", "0")) or int(problem.conf.get("samples_per_cta", 0))
-                    or choose_spb(self.B, self.L, sms))
-        assert 4 <= self.spb <= SPB
+        spec = problem.base_model.spec
+        self.dtype = a.dtype
+        # the paper's (3, 5, 64) net in fp32 runs the specialised kernels; every other shape and all of fp64 run the
+        # generic CUDA-core kernel (csrc/mnist_generic.cu)
+        self.generic = not (self.dtype == torch.float32 and mnist_kernel_is_paper_shape(spec)) \
+            or os.environ.get("NNDT_MNIST_GENERIC") == "1"
+        if self.generic:
+            d64 = int(self.dtype == torch.float64)
+            fits8 = self.ext.convnet_generic_smem_bytes(spec.num_filters, spec.kernel_size, spec.linear_width, d64, 8) <= 200 * 1024
+            want = int(os.environ.get("NNDT_GENERIC_SPB", "0")) or (8 if fits8 and self.L * -(-self.B // 8) >= sms // 2 else 4)
+            self.spb = 8 if (want == 8 and fits8) else 4
+        else:
+            self.spb = (int(os.environ.get("NNDT_SPB", "0")) or int(problem.conf.get("samples_per_cta", 0))
+                        or choose_spb(self.B, self.L, sms))
+            assert 4 <= self.spb <= SPB
         self.S = -(-self.B // self.spb)
         sh = problem.shards
         self.x = sh.x.reshape(sh.x.shape[0], -1).contiguous()
@@ -52,7 +64,7 @@ class FusedMnist:
         self.calls = torch.zeros(self.L, dtype=torch.int32, device=dev)
         self.arrive = torch.zeros(self.L, dtype=torch.int32, device=dev)
         self.owns_calls = True      # the training kernel advances the draw counters (not the consensus kernels)
-        self.grad_part = torch.zeros(self.L, self.S, self.n_pad, dtype=torch.float32, device=dev)
+        self.grad_part = torch.zeros(self.L, self.S, self.n_pad, dtype=self.dtype, device=dev)
         self.loss_part = torch.zeros(self.L, self.S, dtype=torch.float32, device=dev)
         off = {s.name: s.offset for s in a.layout.slots}
         names = [s.name for s in a.layout.slots]
@@ -66,7 +78,9 @@ class FusedMnist:
             shard_off=self.shard_off.data_ptr(), shard_len=self.shard_len.data_ptr(),
             calls=self.calls.data_ptr(), arrive=self.arrive.data_ptr(),
             grad_part=self.grad_part.data_ptr(), loss_part=self.loss_part.data_ptr(),
-            spb=self.spb, S=self.S, tune=int(os.environ.get("NNDT_MNIST_TUNE", "1")))
+            spb=self.spb, S=self.S, tune=int(os.environ.get("NNDT_MNIST_TUNE", "1")),
+            generic=int(self.generic), num_filters=spec.num_filters, kernel_size=spec.kernel_size,
+            linear_width=spec.linear_width, dtype64=int(self.dtype == torch.float64))
         if os.environ.get("NNDT_STEP_PROF") == "1":     # scripts/profile_round_phases.py --per-step
             self.step_prof = torch.zeros(self.L * self.S, 64, dtype=torch.int64, device=dev)
             self.base["step_prof"] = self.step_prof.data_ptr()
@@ -85,7 +99,7 @@ class FusedMnist:
 
     def supports_round_kernel(self, opt) -> bool:
         """The cluster kernel needs the node's S batch slices in one cluster (S <= 8 CTAs) and fp32 state."""
-        return (opt.alg_name == "dinno" and self.spb == SPB and self.S <= 8 and 1 <= opt.pits <= self.MAX_ROUND_STEPS
+        return (not self.generic and opt.alg_name == "dinno" and self.spb == SPB and self.S <= 8 and 1 <= opt.pits <= self.MAX_ROUND_STEPS
                 and self.pr.arena.dtype == torch.float32 and self.ext.dinno_round_max_clusters(self.S) >= 1)
 
     def round_op(self, cons_dict, stage_set=None):
@@ -112,7 +126,7 @@ class FusedMnist:
         self.launch()
         torch.sum(self.grad_part, dim=1, out=pr.arena.grad)
         pr.count_draws_all(1)
-        pr.last_losses = self.loss_part.sum(1)
+        pr.last_losses = self.loss_part.sum(1).to(self.dtype)
         return pr.last_losses
 
     def sync_calls_from_host(self):
@@ -269,7 +283,7 @@ class FusedMnist:
         self.vx = vx if vx.dtype == torch.uint8 else vx.to(torch.float32).contiguous()
         self.vy = pr.val.y.to(torch.int64).contiguous()
         V = len(pr.val)
-        self.val_loss = torch.zeros(self.L, V, dtype=torch.float32, device=dev)
+        self.val_loss = torch.zeros(self.L, V, dtype=self.dtype, device=dev)
         self.val_correct = torch.zeros(self.L, V, dtype=torch.uint8, device=dev)
         mean, std = pr.val.norm if pr.val.norm is not None else (0.0, 1.0)
         sms = torch.cuda.get_device_properties(dev).multi_processor_count

@@ -23,7 +23,8 @@ import torch
 from .engine import ConsensusEngine
 
 MAX_ROUNDS_PER_GRAPH = 64
-PULL_ROUNDS_PER_GRAPH = 16     # host-fed (gpu_pull) rounds captured per graph, staging overlapped inside the graph
+PULL_ROUNDS_PER_GRAPH = 64     # host-fed / staged rounds captured per graph (staging kernel forked inside the graph); a
+                               # production chunk (evaluate_frequency rounds, 20 in the PAPER configs) is ONE graph launch
 
 
 def _nvtx(name):
@@ -201,22 +202,28 @@ class RoundProgram:
             self._join_publish()
         return g
 
-    def _run_pull_graphs(self, rounds: int):
+    def _pull_graph(self, r: int, parity: int):
+        key = (r, parity)
+        g = self._pull_graphs.get(key)
+        if g is None:
+            g = self._pull_graphs[key] = self._capture_pull_graph(r, parity)
+        return g
+
+    def _run_pull_graphs(self, rounds: int, capture_only: bool = False):
         fz = self.pr.fused
         if not self._pull_primed:
             fz.gather_ops[self._pull_parity].launch()      # stage the very first round
             self._pull_primed = True
-        left = rounds
+        left, parity = rounds, self._pull_parity
         while left > 0:
             r = min(left, PULL_ROUNDS_PER_GRAPH)
-            key = (r, self._pull_parity)
-            g = self._pull_graphs.get(key)
-            if g is None:
-                g = self._pull_graphs[key] = self._capture_pull_graph(r, self._pull_parity)
-            g.replay()
-            self._pull_parity = (self._pull_parity + r) & 1
-            self._count(r)
+            g = self._pull_graph(r, parity)
+            parity = (parity + r) & 1
             left -= r
+            if not capture_only:
+                g.replay()
+                self._pull_parity = parity
+                self._count(r)
 
     def _run_host_fed(self, rounds: int):
         """Host-fed rounds.  ``gpu_pull`` (default): multi-round graphs with the staging kernel forked inside
@@ -244,6 +251,33 @@ class RoundProgram:
         self._runner.run(rounds)
         self._count(rounds)
 
+    def _resident_graph(self, r: int):
+        g = self._graphs.get(r)
+        if g is None:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _ in range(r):
+                    _round_ops(self.opt, self.eng, self.grads, self.round_op(), self._publish_forked)
+                self._join_publish()
+            self._graphs[r] = g
+        return g
+
+    def prepare(self, rounds: int):
+        """Capture (without executing) every CUDA graph that ``run(rounds)`` will replay from the current state, so a
+        following ``run`` issues graph launches only."""
+        if not self.capturable:
+            return
+        if self.host_mode:
+            fz = self.pr.fused
+            if fz.host_feed["mode"] == "gpu_pull" and os.environ.get("NNDT_PULL_DRIVER", self.pr.conf.get("host_pull_driver", "graph")) == "graph":
+                self._run_pull_graphs(rounds, capture_only=True)
+            return
+        left = rounds
+        while left > 0:
+            r = min(left, MAX_ROUNDS_PER_GRAPH)
+            self._resident_graph(r)
+            left -= r
+
     def run(self, rounds: int):
         """Execute ``rounds`` consecutive rounds starting at the device round counter."""
         if self.host_mode:
@@ -252,15 +286,7 @@ class RoundProgram:
         while left > 0:
             r = min(left, MAX_ROUNDS_PER_GRAPH)
             if self.capturable:
-                g = self._graphs.get(r)
-                if g is None:
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
-                        for _ in range(r):
-                            _round_ops(self.opt, self.eng, self.grads, self.round_op(), self._publish_forked)
-                        self._join_publish()
-                    self._graphs[r] = g
-                g.replay()
+                self._resident_graph(r).replay()
             else:
                 for _ in range(r):
                     _round_ops(self.opt, self.eng, self.grads, self.round_op())

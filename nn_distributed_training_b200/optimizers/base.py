@@ -159,6 +159,22 @@ class ConsensusOptimizer:
                 self._round(self.k)
                 self.k += 1
 
+    def prepare_rounds(self, n: int):
+        """Capture (without executing a round) the CUDA graphs that ``run_rounds(n)`` will replay, so that call is graph
+        launches only.  No-op on the PyTorch path."""
+        n = min(int(n), self.oits - self.k)
+        if n <= 0 or not self._use_engine():
+            return
+        from ..ops.round_program import RoundProgram
+        prog = getattr(self, "_program", None)
+        if prog is None:
+            prog = self._program = RoundProgram(self)
+            if self.alg_name == "dsgt":
+                if self.init_grads and not self._initialised:
+                    prog.dsgt_init()
+                self._initialised = True
+        prog.prepare(n)
+
     def _use_engine(self) -> bool:
         """Fused sm_100a consensus kernels: any arena problem on a CUDA device with the
         synchronous (Jacobi) update order; the PyTorch ops remain for CPU/gloo, for

@@ -78,3 +78,39 @@ class SymmetricBuffer:
         self.local = t.view(self.shape)
         self.peer_ptrs = ptrs
         self.how = "cuda_ipc"
+
+
+class DeviceBarrier:
+    """All-rank barrier executed ON THE DEVICE (csrc/consensus.cu: rank_barrier_kernel): every rank stores an epoch into
+    its slot of every peer's array and spins until all peers did.  Enqueued on the current stream, so whatever is enqueued
+    behind it starts within an NVLink flag latency on every GPU — host-side barrier exit skew (tens of microseconds, and
+    milliseconds when NVML or Python run between the barrier and the first launch) never reaches the device timeline.
+    ``gate=True`` makes the kernel first wait for ``open_gate()``: the host enqueues the whole timed region behind the
+    barrier and only then releases it, so launch latency is not timed either."""
+
+    def __init__(self, ctx):
+        from ..ops import load_ext
+
+        self.ctx = ctx
+        self.ext = load_ext(required=True)
+        w = max(ctx.world_size, 1)
+        self.buf = SymmetricBuffer((w,), torch.int32, ctx)
+        self.peer_slot = torch.tensor([p + 4 * ctx.rank for p in self.buf.peer_ptrs] + [0] * (w - len(self.buf.peer_ptrs)),
+                                      dtype=torch.int64, device=ctx.device)
+        self.err = torch.zeros(1, dtype=torch.int32, device=ctx.device)
+        self.gate = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.epoch = 0
+
+    def enqueue(self, gate: bool = False):
+        self.epoch += 1
+        if gate:
+            self.gate.zero_()
+        self.ext.rank_barrier(self.buf.local.data_ptr(), self.peer_slot.data_ptr(), max(self.ctx.world_size, 1), self.ctx.rank,
+                              self.epoch, self.gate.data_ptr() if gate else 0, self.err.data_ptr())
+
+    def open_gate(self):
+        self.gate.fill_(1)
+
+    def check(self):
+        if int(self.err.item()) != 0:
+            raise RuntimeError("device rank barrier timed out")

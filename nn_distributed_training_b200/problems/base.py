@@ -276,10 +276,16 @@ class ConsensusProblem:
             raise ValueError(f"unknown backend {want!r}")
         if want == "torch":
             return "torch"
-        ok = self.device.type == "cuda" and self.dtype == torch.float32 and self._fused_supported()
+        ok = self.device.type == "cuda" and self.dtype in (torch.float32, torch.float64) and self._fused_supported()
         if want == "fused" and not ok:
             raise RuntimeError("fused sm_100a backend requested but unsupported for this "
-                               "device/dtype/model (needs CUDA, fp32 and a kernel-backed model spec)")
+                               "device/dtype/model (needs CUDA and a kernel-backed model spec / dtype)")
+        if not ok and self.device.type == "cuda" and self.ctx.is_main:
+            # never a silent fallback on a GPU box: say which model runs autograd + library kernels and why
+            print(f"[nndt] WARNING: no fused forward/backward kernel for {type(self.base_model).__name__} "
+                  f"(spec={getattr(self.base_model, 'spec', None)}, dtype={self.dtype}, loss={type(self.base_loss).__name__}): "
+                  "forward/backward falls back to PyTorch autograd (cuDNN/cuBLAS); the consensus kernels stay fused",
+                  flush=True)
         return "fused" if ok else "torch"
 
     def _setup_fused(self):  # pragma: no cover - overridden

@@ -100,7 +100,7 @@ class DistMNISTProblem(ConsensusProblem):
         if not isinstance(spec, ConvNetSpec) or not isinstance(self.base_loss, torch.nn.NLLLoss):
             return False
         from ..ops import fused_available, mnist_kernel_supports
-        return fused_available() and mnist_kernel_supports(spec, self.train_batch_size)
+        return fused_available() and mnist_kernel_supports(spec, self.train_batch_size, self.dtype)
 
     def _setup_fused(self):
         from ..ops.mnist_fused import FusedMnist
