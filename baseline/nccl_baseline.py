@@ -1,0 +1,171 @@
+"""'The NCCL baseline' (BASELINE.md (b)): the DiNNO update rules of dist_mnist_PAPER written the way a
+library-only solution would be on 8 GPUs — one rank per GPU, PyTorch ops + cuDNN/cuBLAS + NCCL, no custom kernels:
+
+* the L local nodes' conv nets are evaluated TOGETHER: grouped cuDNN convolution (groups = L), batched cuBLAS GEMMs
+  (``torch.bmm``) for the two linear layers, one autograd backward for all nodes;
+* the neighbor exchange is an NCCL ``all_gather`` of the [L, n] parameter block followed by ONE cuBLAS GEMM with the
+  local rows of the adjacency matrix (``A_local @ theta_all``) — the textbook dense formulation of "sum over neighbors";
+* dual ascent, the augmented-Lagrangian gradient and Adam are flat elementwise torch ops on [L, n];
+* the whole round is captured in a CUDA graph when NCCL capture works on the box (falls back to eager launches).
+
+This is deliberately a *good* library implementation (the reference itself is a Python loop over nodes and parameter
+tensors, ~800 launches per round): it is what the fused sm_100a path has to beat.  fp32.
+Update equations: optimizers/dinno.py:74-125 of the reference (closed form).
+"""
+from __future__ import annotations
+
+import json
+import math
+
+import numpy as np
+
+
+def run(args, metric, nodes_per_gpu, batch, pits, opt_conf, shard_fn):
+    import networkx as nx
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    from nn_distributed_training_b200.data.mnist import MNIST_MEAN, MNIST_STD
+    from nn_distributed_training_b200.models import MNISTConvNet
+    from nn_distributed_training_b200.parallel.context import DistContext
+
+    ctx = DistContext.from_env(use_cuda=True)
+    dev = ctx.device
+    G = ctx.world_size
+    L, N = nodes_per_gpu, nodes_per_gpu * G
+    lo = ctx.rank * L
+    W, K = max(args.warmup, 3), args.steps
+    oc = opt_conf(W + 2 * K + 8)
+    graph = nx.cycle_graph(N)
+    A = torch.zeros(L, N, device=dev)
+    for l in range(L):
+        for j in graph.neighbors(lo + l):
+            A[l, j] = 1.0
+    deg = A.sum(1, keepdim=True)
+
+    # ---- parameters: one flat [L, n] leaf; layer tensors are views ----------------------------------------
+    torch.manual_seed(0)
+    base = MNISTConvNet(3, 5, 64)
+    shapes = [tuple(p.shape) for p in base.parameters()]
+    sizes = [int(np.prod(s)) for s in shapes]
+    n = sum(sizes)
+    flat0 = torch.cat([p.detach().reshape(-1) for p in base.parameters()])
+    theta = flat0.to(dev).repeat(L, 1).contiguous().requires_grad_(True)
+    offs = np.cumsum([0] + sizes)
+
+    def views(th):
+        wc = th[:, offs[0]:offs[1]].reshape(L * 3, 1, 5, 5)
+        bc = th[:, offs[1]:offs[2]].reshape(L * 3)
+        w1 = th[:, offs[2]:offs[3]].reshape(L, 64, 432)
+        b1 = th[:, offs[3]:offs[4]].reshape(L, 1, 64)
+        w2 = th[:, offs[4]:offs[5]].reshape(L, 10, 64)
+        b2 = th[:, offs[5]:offs[6]].reshape(L, 1, 10)
+        return wc, bc, w1, b1, w2, b2
+
+    # ---- data: device-resident uint8 shards, random rows per step ---------------------------------------------
+    M = 6000
+    xs = torch.stack([shard_fn(M, 100 + lo + l, [(lo + l) % 10]).x.reshape(M, 784) for l in range(L)]).to(dev)   # [L, M, 784] u8
+    ys = torch.stack([shard_fn(M, 100 + lo + l, [(lo + l) % 10]).y for l in range(L)]).to(dev)                    # [L, M]
+    ar = torch.arange(L, device=dev).unsqueeze(1)
+
+    def loss_fn(th):
+        idx = torch.randint(0, M, (L, batch), device=dev)
+        x = xs[ar, idx].to(torch.float32).div_(255.0).sub_(MNIST_MEAN).div_(MNIST_STD)      # [L, B, 784]
+        y = ys[ar, idx]                                                                       # [L, B]
+        wc, bc, w1, b1, w2, b2 = views(th)
+        z = F.conv2d(x.reshape(L, batch, 28, 28).transpose(0, 1), wc, bc, groups=L)           # [B, 3L, 24, 24]
+        z = F.max_pool2d(F.relu(z), 2).reshape(batch, L, 432).transpose(0, 1)                 # [L, B, 432]
+        hdn = F.relu(torch.baddbmm(b1, z, w1.transpose(1, 2)))
+        out = F.log_softmax(torch.baddbmm(b2, hdn, w2.transpose(1, 2)), dim=2)               # [L, B, 10]
+        return F.nll_loss(out.reshape(L * batch, 10), y.reshape(-1), reduction="sum") / batch
+
+    dual = torch.zeros(L, n, device=dev)
+    delta = torch.zeros(L, n, device=dev)
+    thk = torch.zeros(L, n, device=dev)
+    m = torch.zeros(L, n, device=dev)
+    v = torch.zeros(L, n, device=dev)
+    gathered = torch.zeros(N, n, device=dev)
+    rho_t = torch.zeros((), device=dev)
+    lr_t = torch.zeros((), device=dev)
+    rho0, rs = oc["rho_init"], oc["rho_scaling"]
+    lrs = np.logspace(math.log10(oc["primal_lr_start"]), math.log10(oc["primal_lr_finish"]), oc["outer_iterations"])
+
+    def round_body():
+        with torch.no_grad():
+            thk.copy_(theta)
+            if G > 1:
+                dist.all_gather_into_tensor(gathered, thk)
+            else:
+                gathered.copy_(thk)
+            torch.mm(A, gathered, out=delta)                  # sum of neighbor rows: one cuBLAS GEMM
+            delta.addcmul_(deg.expand_as(thk), thk, value=-1.0)   # delta = sum_j (theta_j - theta_i)
+            dual.addcmul_(delta, rho_t.expand_as(delta), value=-1.0)
+            m.zero_(); v.zero_()
+        for p in range(pits):
+            loss = loss_fn(theta)
+            (g,) = torch.autograd.grad(loss, theta)
+            with torch.no_grad():
+                g = g + dual + 2.0 * rho_t * deg * (theta - thk) - rho_t * delta
+                t = p + 1
+                m.mul_(0.9).add_(g, alpha=0.1)
+                v.mul_(0.999).addcmul_(g, g, value=0.001)
+                den = (v.sqrt() / math.sqrt(1 - 0.999 ** t)).add_(1e-8)
+                theta.addcdiv_(m * (lr_t / (1 - 0.9 ** t)), den, value=-1.0)
+
+    k = [0]
+
+    def set_round():
+        rho_t.fill_(rho0 * rs ** (k[0] + 1))
+        lr_t.fill_(float(lrs[min(k[0], len(lrs) - 1)]))
+        k[0] += 1
+
+    # ---- eager warm-up, then try a CUDA graph of one round -----------------------------------------------------
+    for _ in range(W):
+        set_round(); round_body()
+    torch.cuda.synchronize(); ctx.barrier()
+    graph_ok, g = False, None
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            set_round(); round_body()
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            round_body()
+        for _ in range(3):
+            set_round(); g.replay()
+        torch.cuda.synchronize()
+        graph_ok = True
+    except Exception as e:  # noqa: BLE001
+        graph_err = repr(e)[:200]
+        g = None
+        torch.cuda.synchronize()
+
+    def timed(use_graph):
+        torch.cuda.synchronize(); ctx.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            set_round()
+            if use_graph:
+                g.replay()
+            else:
+                round_body()
+        e1.record(); torch.cuda.synchronize(); ctx.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        return float(ctx.all_reduce_max(t).item())
+
+    ms_eager = timed(False)
+    ms_graph = timed(True) if graph_ok else None
+    ms = min(ms_eager, ms_graph) if ms_graph is not None else ms_eager
+    if ctx.is_main:
+        print(json.dumps({"metric": metric, "impl": "nccl_baseline (PyTorch: grouped cuDNN conv + bmm for all local nodes, NCCL all_gather + "
+                          "cuBLAS adjacency GEMM, elementwise Adam" + (", CUDA graph" if graph_ok else ", eager") + ")",
+                          "value": N * K / (ms / 1e3), "unit": "node-rounds/s", "n_gpus": G, "steps": K, "warmup": W,
+                          "ms_per_step": ms / K, "ms_per_step_eager": ms_eager / K,
+                          "ms_per_step_cuda_graph": None if ms_graph is None else ms_graph / K,
+                          "cuda_graph": graph_ok if graph_ok else graph_err, "dtype": "fp32", "data": "synthetic",
+                          "higher_is_better": True, "scaling": "weak", "final_loss_finite": bool(torch.isfinite(theta).all())}))
+    if dist.is_initialized():
+        dist.destroy_process_group()

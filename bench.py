@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Headline benchmark: consensus rounds/sec of DiNNO on the dist_mnist_PAPER config.
 
-    python bench.py --gpus N --steps K --warmup W [--impl ours|reference]
+    python bench.py --gpus N --steps K --warmup W [--impl ours|reference|nccl] [--dtype fp64|fp32]
     (N > 1: launched by the driver through torch.distributed.run, one rank per GPU)
 
 Config (reference: experiments/dist_mnist_PAPER.yaml problem1): MNISTConvNet(3,5,64),
@@ -14,14 +14,31 @@ rounds/sec x number of graph nodes (whole job).  Synthetic MNIST-shaped uint8 da
 random-init weights (no dataset can be downloaded); evaluation is excluded from the timed
 region in both arms.
 
+Precision.  The reference runs float64 end to end (experiments/dist_mnist_ex.py:19), so the
+headline of BOTH arms is float64 (``--dtype fp64``, the default): ours = the hand-written fp64
+forward/backward kernel (csrc/mnist_generic.cu) + the fp64 instantiation of the fused consensus
+kernels.  ``extra.fp32`` carries the same measurement at float32 for both arms (ours = the fp32
+tensor-core kernels; reference = the same stock classes under torch.set_default_dtype(float32)).
+
 * ``value``  — device-timed (CUDA events on the launching stream, max over ranks), shards
   resident in HBM (the framework's native pipeline); each GPU's shard set is sized > L2 and
   rows are gathered at random, so inputs are not L2-resident between iterations.
-* ``e2e``    — same metric through the public API ``DiNNO(problem, device, conf).train()``
+* ``e2e``    — same metric through the public API ``DiNNO(problem, device, conf).run_rounds``
   with the host-fed input pipeline: every round copies that round's minibatches from
   pinned host memory (H2D) and reads the per-node losses back (D2H).
+* timing protocol — W warm-up rounds, then the CUDA graphs of the K timed rounds are captured
+  (not run); every rank enqueues [device rank barrier, event, K rounds, event] behind a gate
+  kernel and the host opens the gate: the K rounds start within an NVLink flag latency on all
+  GPUs and no host-side skew (NCCL barrier exit, NVML, Python) is inside the events.
+* ``extra.one_per_gpu`` — the communication-bound regime (N > 1): ONE graph node per GPU,
+  ring / complete (NVLS) / random graph x DiNNO / DSGD / DSGT, every edge crosses NVLink.
+* ``extra.multi_gpu_selfcheck`` — (N > 1, untimed) the distributed run's parameters after a few
+  rounds against a single-process recomputation on rank 0.
 * ``--impl reference`` — the unmodified reference (baseline/_ref) through its own public API
-  (DistMNISTProblem + DiNNO(...).train(profiler=hook)), stock fp64, all nodes on one device.
+  (DistMNISTProblem + DiNNO(...).train(profiler=hook)), all nodes on one device.
+* ``--impl nccl`` — one-rank-per-GPU PyTorch + NCCL re-expression (batched cuDNN/cuBLAS
+  forward/backward of all local nodes, all_gather of the parameter rows, torch elementwise
+  mixing/Adam, CUDA-graph captured): "the NCCL baseline" a library-only solution would be.
 """
 from __future__ import annotations
 
@@ -40,26 +57,42 @@ if ROOT not in sys.path:
 
 NODES_PER_GPU = 10
 BATCH = 64
-REF_MAX_SECONDS = 150.0
+REF_MAX_SECONDS = 120.0
 REF_SEC_PER_NODE_ROUND = 0.00465
 PITS = 2
 SAMPLES_PER_NODE = 22000          # 10 nodes x 22000 x 784 B = 172 MB of uint8 rows per GPU (> 126 MB L2)
 REF_SAMPLES_PER_NODE = 6000       # the paper's 60000 / 10 (the reference streams from host memory anyway)
 PAPER_ROUNDS = 2000
+METRIC = "consensus node-rounds/sec (DiNNO, dist_mnist_PAPER; rounds/sec x graph nodes)"
 
 
-def opt_conf(outer_iterations: int):
+def opt_conf(outer_iterations: int, alg: str = "dinno"):
+    if alg == "dsgd":       # experiments/dist_mnist_PAPER.yaml problem3
+        return {"alg_name": "dsgd", "alpha0": 0.005, "mu": 0.001, "outer_iterations": outer_iterations, "profile": False}
+    if alg == "dsgt":       # problem2
+        return {"alg_name": "dsgt", "alpha": 0.005, "init_grads": True, "outer_iterations": outer_iterations, "profile": False}
     return {"alg_name": "dinno", "rho_init": 0.5, "rho_scaling": 1.0003, "outer_iterations": outer_iterations,
             "primal_iterations": PITS, "primal_optimizer": "adam", "persistant_primal_opt": False,
             "primal_lr_start": 0.005, "primal_lr_finish": 0.0005, "lr_decay_type": "log", "profile": False}
 
 
 def prob_conf(oc, eval_every, extra=None):
-    c = {"problem_name": "dinno", "train_batch_size": BATCH, "val_batch_size": 128, "verbose_evals": True,
+    c = {"problem_name": oc["alg_name"], "train_batch_size": BATCH, "val_batch_size": 128, "verbose_evals": True,
          "metrics": ["forward_pass_count", "validation_loss", "consensus_error", "top1_accuracy", "current_epoch"],
          "metrics_config": {"evaluate_frequency": eval_every}, "optimizer_config": oc}
     c.update(extra or {})
     return c
+
+
+def headline_config(n_gpus: int):
+    """Identical in both arms (the driver compares the dicts)."""
+    n = NODES_PER_GPU * n_gpus
+    return {"model": "MNISTConvNet(3,5,64) 28440 params", "yaml": "dist_mnist_PAPER.yaml/problem1 (DiNNO)",
+            "graph": f"cycle, {n} nodes ({NODES_PER_GPU} per GPU)", "global_batch": BATCH * n,
+            "primal_iterations": PITS, "seq_len": None,
+            "parallelism": f"consensus graph, {NODES_PER_GPU} nodes/GPU x {n_gpus} GPU",
+            "eval": "excluded from timed region",
+            "l2": "inputs > L2 or streamed from host memory every step; no flush"}
 
 
 # ------------------------------------------------------------------ clocks ----
@@ -79,6 +112,7 @@ class ClockSampler:
         except Exception:  # noqa: BLE001
             self._h = None
         self._t = threading.Thread(target=self._loop, daemon=True)
+        self.active = False
 
     def _once(self):
         if self._h is None:
@@ -98,11 +132,12 @@ class ClockSampler:
 
     def _loop(self):
         while not self._stop.is_set():
-            self._once()
-            time.sleep(0.002)
+            if self.active:
+                self._once()
+            time.sleep(0.0005)
 
     def start(self):
-        self._once()
+        """Spawn the sampling thread (call BEFORE the barrier that precedes the timed region)."""
         self._t.start()
 
     def stop(self):
@@ -114,8 +149,8 @@ class ClockSampler:
 
 
 class StepTimer:
-    """``profiler.step()`` hook: records a CUDA event after every round; the timed region is
-    rounds [warmup, warmup+steps)."""
+    """``profiler.step()`` hook of the reference arm: records a CUDA event after every round; the timed region
+    is rounds [warmup, warmup+steps)."""
 
     def __init__(self, warmup, steps, on_start=None, on_stop=None):
         import torch
@@ -149,27 +184,15 @@ class StepTimer:
 
 
 # -------------------------------------------------------------------- ours ----
-def build_problem(ctx, n_nodes, oc, eval_every, extra=None, samples_per_node=SAMPLES_PER_NODE, backend="fused"):
-    import networkx as nx
-    import torch
-    from nn_distributed_training_b200.data.mnist import synthetic_mnist
-    from nn_distributed_training_b200.data.shards import Shard
-    from nn_distributed_training_b200.models import MNISTConvNet
-    from nn_distributed_training_b200.parallel.context import Placement
-    from nn_distributed_training_b200.problems.dist_mnist_problem import DistMNISTProblem
+_SHARD_CACHE = {}
 
-    pl = Placement(n_nodes, ctx.world_size, ctx.rank)
-    train = []
-    for g in range(n_nodes):
-        if pl.is_local(g):
-            train.append(synthetic_mnist(samples_per_node, seed=100 + g, classes=[g % 10]))
-        else:
-            train.append(_Stub(samples_per_node))
-    val = synthetic_mnist(10000, seed=1)
-    torch.manual_seed(0)
-    base = MNISTConvNet(3, 5, 64)
-    return DistMNISTProblem(nx.cycle_graph(n_nodes), base, torch.nn.NLLLoss(), train, val, ctx.device,
-                            prob_conf(oc, eval_every, extra), ctx=ctx, backend=backend)
+
+def _shard(n, seed, classes):
+    from nn_distributed_training_b200.data.mnist import synthetic_mnist
+    key = (n, seed, tuple(classes) if classes is not None else None)
+    if key not in _SHARD_CACHE:
+        _SHARD_CACHE[key] = synthetic_mnist(n, seed=seed, classes=classes)
+    return _SHARD_CACHE[key]
 
 
 class _Stub:
@@ -180,107 +203,254 @@ class _Stub:
         return self.n
 
 
-def run_ours(args):
+def build_problem(ctx, graph, oc, eval_every, extra=None, samples_per_node=SAMPLES_PER_NODE, backend="fused",
+                  dtype="fp32"):
     import torch
-    import torch.distributed as dist
-    from nn_distributed_training_b200.optimizers import DiNNO
-    from nn_distributed_training_b200.parallel.context import DistContext
+    from nn_distributed_training_b200.models import MNISTConvNet
+    from nn_distributed_training_b200.parallel.context import Placement
+    from nn_distributed_training_b200.problems.dist_mnist_problem import DistMNISTProblem
 
-    ctx = DistContext.from_env(use_cuda=True)
-    assert ctx.world_size == args.gpus, f"launched with WORLD_SIZE={ctx.world_size} but --gpus {args.gpus}"
-    n_nodes = NODES_PER_GPU * args.gpus
-    W, K = args.warmup, args.steps
-    oits = max(PAPER_ROUNDS, 4 * (W + K) + 64)
-    dev = ctx.device
+    n_nodes = graph.number_of_nodes()
+    pl = Placement(n_nodes, ctx.world_size, ctx.rank)
+    train = [(_shard(samples_per_node, 100 + g, [g % 10]) if pl.is_local(g) else _Stub(samples_per_node))
+             for g in range(n_nodes)]
+    val = _shard(10000, 1, None)
+    torch.manual_seed(0)
+    base = MNISTConvNet(3, 5, 64)
+    if dtype == "fp64":
+        base = base.double()
+    return DistMNISTProblem(graph, base, torch.nn.NLLLoss(), train, val, ctx.device,
+                            prob_conf(oc, eval_every, extra), ctx=ctx, backend=backend)
 
-    def maxreduce(x):
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        return float(ctx.all_reduce_max(t).item())
 
-    # ---------------- device-timed, resident shards ----------------------------
-    pipeline = os.environ.get("NNDT_BENCH_PIPELINE", "auto")      # auto (= staged-resident) | resident (A/B switch)
-    pr = build_problem(ctx, n_nodes, opt_conf(oits), eval_every=10 ** 9, extra={"input_pipeline": pipeline})
-    opt = DiNNO(pr, dev, pr.conf["optimizer_config"])
-    opt.run_rounds(max(W, 3))            # warm-up
-    n_warm = 2 if K % 2 else 1           # an untimed pass with the timed call's chunking (and staging parity): every
-    for _ in range(n_warm):              # CUDA graph the timed region replays is captured here
+class Harness:
+    """Aligned device timing of ``opt.run_rounds(K)`` (see the module docstring)."""
+
+    def __init__(self, ctx):
+        import torch
+        from nn_distributed_training_b200.parallel.symm import DeviceBarrier
+        self.torch, self.ctx = torch, ctx
+        self.bar = DeviceBarrier(ctx)
+
+    def maxreduce(self, x):
+        torch = self.torch
+        t = torch.tensor([x], dtype=torch.float64, device=self.ctx.device)
+        return float(self.ctx.all_reduce_max(t).item())
+
+    def time_rounds(self, opt, K, sampler=None):
+        torch, ctx = self.torch, self.ctx
+        opt.prepare_rounds(K)                 # capture (not run) the graphs of the timed call
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ctx.barrier()
+        if sampler is not None:
+            sampler.active = True
+        t0 = time.perf_counter()
+        self.bar.enqueue(gate=True)           # spins until the host opens the gate, then aligns all ranks on the device
+        e0.record()
         opt.run_rounds(K)
-    sampler = ClockSampler(dev.index or 0)
-    torch.cuda.synchronize()
-    ctx.barrier()
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    opt.run_rounds(K)
-    e1.record()
-    torch.cuda.synchronize()
-    ctx.barrier()
-    clocks = sampler.stop()
-    ms = maxreduce(e0.elapsed_time(e1))
-    launches = K * opt._program.launches_per_round()
-    opt_pipeline = opt._program.pipeline + (" (HBM-resident shards; the staging kernel gathers the next round's rows)" if opt._program.pipeline == "staged" else "")
-    round_kernel = "dinno_round_kernel (1 cluster launch/round)" if opt._program.round_op() is not None else "mnist_kernel + dinno_update_kernel per primal step"
-    # model quality after the rounds run so far (not timed)
-    pr.evaluate_metrics()
-    acc = float(pr.metrics["top1_accuracy"][-1].mean())
-    rounds_done = opt.k
-    opt._program.eng.check()
-    symm_how = opt._program.eng.pub_buf.how
-    del opt, pr
+        e1.record()
+        self.bar.open_gate()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        if sampler is not None:
+            sampler.active = False
+        ctx.barrier()
+        return self.maxreduce(e0.elapsed_time(e1)), self.maxreduce(wall * 1e3)
+
+
+def _cycle(n):
+    import networkx as nx
+    return nx.cycle_graph(n) if n > 2 else nx.path_graph(n)
+
+
+def measure_headline(h, ctx, args, dtype, sampler=None, probe=False):
+    """value (resident/staged shards) + e2e (host-fed) of the headline config at ``dtype``."""
+    import torch
+    from nn_distributed_training_b200.optimizers import DiNNO
+
+    n_nodes = NODES_PER_GPU * args.gpus
+    W, K = max(args.warmup, 3), args.steps
+    oits = max(PAPER_ROUNDS, 8 * (W + K) + 1024)
+    dev = ctx.device
+    pipeline = os.environ.get("NNDT_BENCH_PIPELINE", "auto")      # auto (= staged-resident) | resident (A/B switch)
+    pr = build_problem(ctx, _cycle(n_nodes), opt_conf(oits), 10 ** 9, extra={"input_pipeline": pipeline}, dtype=dtype)
+    opt = DiNNO(pr, dev, pr.conf["optimizer_config"])
+    opt.run_rounds(W)                     # warm-up (captures + runs its own graph)
+    ms, _ = h.time_rounds(opt, K, sampler)
+    prog = opt._program
+    out = {"ms_per_step": ms / K, "value": n_nodes * K / (ms / 1e3), "launches": K * prog.launches_per_round(),
+           "pipeline": prog.pipeline, "symm": prog.eng.pub_buf.how, "flags": prog.eng.flag_mode,
+           "fwd_bwd_kernel": ("convnet_generic_kernel<%s> (CUDA cores)" % ("double" if dtype == "fp64" else "float"))
+           if pr.fused.generic else getattr(pr.fused, "kernel_name", "mnist_kernel (3xTF32 mma)")}
+    if probe:   # per-call fixed cost: t(K) = intercept + slope K  (K = 20 is the production chunk, evaluate_frequency 20)
+        pts = []
+        for kk in (4, 20, 64, 256):
+            m, _ = h.time_rounds(opt, kk)
+            pts.append((kk, m))
+        n = len(pts); sx = sum(p[0] for p in pts); sy = sum(p[1] for p in pts)
+        sxx = sum(p[0] ** 2 for p in pts); sxy = sum(p[0] * p[1] for p in pts)
+        slope = (n * sxy - sx * sy) / (n * sxx - sx * sx)
+        out["fixed_cost_probe"] = {"ms_by_K": {str(k): round(m, 4) for k, m in pts}, "slope_ms_per_round": round(slope, 5),
+                                   "intercept_ms": round((sy - slope * sx) / n, 4)}
+    pr.evaluate_metrics()                 # model quality after the rounds run so far (not timed)
+    out["top1_after_rounds"] = float(pr.metrics["top1_accuracy"][-1].mean())
+    out["rounds_done"] = opt.k
+    prog.eng.check()
+    del opt, pr, prog
     torch.cuda.empty_cache()
 
     # ---------------- end to end through the public API, host-fed inputs -------
-    e2e = None
     try:
         W2 = max(W, 6)
-        pr2 = build_problem(ctx, n_nodes, opt_conf(oits), eval_every=10 ** 9, extra={"input_pipeline": "host"})
+        pr2 = build_problem(ctx, _cycle(n_nodes), opt_conf(oits), 10 ** 9, extra={"input_pipeline": "host"}, dtype=dtype)
         opt2 = DiNNO(pr2, dev, pr2.conf["optimizer_config"])
         opt2.run_rounds(W2)                      # warm-up: captures the round graphs, stages the first batch
-        for _ in range(2 if K % 2 else 1):       # untimed pass with the timed call's chunking (and staging parity),
-            opt2.run_rounds(K)                   # so no graph is captured inside the timed region
-        torch.cuda.synchronize()
-        ctx.barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t_wall = time.perf_counter()
-        f0.record()
-        opt2.run_rounds(K)                       # public stepping API: K rounds, each with its H2D copy + D2H loss read
-        f1.record()
-        torch.cuda.synchronize()
-        wall = time.perf_counter() - t_wall
-        ctx.barrier()
-        ms2 = maxreduce(f0.elapsed_time(f1))
+        ms2, wall2 = h.time_rounds(opt2, K)      # public stepping API: K rounds, each with its H2D copy + D2H loss read
         last_losses = pr2.fused.loss_host.sum(1).tolist()
         hf = pr2.fused.host_feed
         if pr2.fused.loader is not None:
             pr2.fused.loader.stop()
-        e2e = {"value": n_nodes * K / (ms2 / 1e3), "unit": "node-rounds/s", "ms_per_step": ms2 / K,
-               "h2d_bytes_per_step": int(hf["h2d_bytes"]), "d2h_bytes_per_step": int(hf["d2h_bytes"]),
-               "api": "DiNNO(problem, device, conf).run_rounds(K) with problem conf input_pipeline=host",
-               "h2d": hf["mode"] + ": every round's uint8 rows + labels are pulled from the pinned host dataset over PCIe",
-               "d2h": ("the training kernel stores every step's per-CTA losses into a pinned host buffer (device-initiated PCIe write)"
-                       if getattr(pr2.fused, "loss_mode", "") == "mirror" else "cudaMemcpyAsync D2H node per round"),
-               "wall_ms_per_step": maxreduce(wall * 1e3) / K, "last_round_losses_read_back": last_losses[:3]}
+        out["e2e"] = {"value": n_nodes * K / (ms2 / 1e3), "unit": "node-rounds/s", "ms_per_step": ms2 / K,
+                      "h2d_bytes_per_step": int(hf["h2d_bytes"]), "d2h_bytes_per_step": int(hf["d2h_bytes"]),
+                      "api": "DiNNO(problem, device, conf).run_rounds(K) with problem conf input_pipeline=host",
+                      "h2d": hf["mode"] + ": every round's uint8 rows + labels are pulled from the pinned host dataset over PCIe",
+                      "d2h": ("the training kernel stores every step's per-CTA losses into a pinned host buffer (device-initiated PCIe write)"
+                              if getattr(pr2.fused, "loss_mode", "") == "mirror" else "cudaMemcpyAsync D2H node per round"),
+                      "wall_ms_per_step": wall2 / K, "last_round_losses_read_back": last_losses[:3]}
+        opt2._program.eng.check()
         del opt2, pr2
     except Exception as e:  # noqa: BLE001
-        e2e = {"error": repr(e)[:300]}
+        out["e2e"] = {"error": repr(e)[:300]}
+    torch.cuda.empty_cache()
+    return out
 
+
+def measure_one_per_gpu(h, ctx, args):
+    """Communication-bound regime: one graph node per GPU, every edge over NVLink (BASELINE.json configs 2-3)."""
+    import networkx as nx
+    import torch
+    from nn_distributed_training_b200.optimizers import build_optimizer
+    G = args.gpus
+    graphs = {"cycle": _cycle(G), "complete": nx.complete_graph(G)}
+    if G >= 4:
+        graphs["random"] = _seeded_random_graph(G)       # Erdos-Renyi p = 0.5, connected (dist_mnist_PAPER-style random graph)
+    K, W = max(args.steps, 40), 5
+    res = {}
+    for gname, g in graphs.items():
+        for alg in ("dinno", "dsgd", "dsgt"):
+            key = f"{alg}/{gname}"
+            try:
+                oc = opt_conf(8 * (W + K) + 64, alg)
+                pr = build_problem(ctx, g, oc, 10 ** 9, samples_per_node=2048, dtype="fp32")
+                opt = build_optimizer(pr, ctx.device, oc)
+                opt.run_rounds(W)
+                ms, _ = h.time_rounds(opt, K)
+                eng = opt._program.eng
+                eng.check()
+                res[key] = {"ms_per_round": round(ms / K, 5), "node_rounds_per_s": round(G * K / (ms / 1e3), 1),
+                            "edges_over_nvlink": g.number_of_edges(), "max_degree": max(dict(g.degree()).values()),
+                            "nvls_sum_mode": bool(eng.sum_mode), "multicast": bool(eng.sum_buf is not None and eng.sum_buf.multicast_ptr)}
+                del opt, pr
+            except Exception as e:  # noqa: BLE001
+                res[key] = {"error": repr(e)[:200]}
+            torch.cuda.empty_cache()
+    return res
+
+
+def _seeded_random_graph(n, p=0.5, seed=7):
+    import networkx as nx
+    for s in range(seed, seed + 200):
+        g = nx.erdos_renyi_graph(n, p, seed=s)
+        if nx.is_connected(g):
+            return g
+    return nx.cycle_graph(n)
+
+
+def selfcheck(ctx, args):
+    """Distributed run == single-process recomputation (what tests/dist_worker.py asserts), at the bench's node count."""
+    import copy
+    import torch
+    from nn_distributed_training_b200.optimizers import build_optimizer
+    from nn_distributed_training_b200.parallel.context import DistContext
+
+    n_nodes, R = NODES_PER_GPU * args.gpus, 6
+    worst, detail = 0.0, {}
+    for alg in ("dinno", "dsgt"):
+        oc = opt_conf(R, alg)
+        pr = build_problem(ctx, _cycle(n_nodes), oc, 10 ** 9, samples_per_node=640)
+        opt = build_optimizer(pr, ctx.device, copy.deepcopy(oc))
+        opt.run_rounds(R)
+        torch.cuda.synchronize()
+        opt._program.eng.check()
+        theta = pr.gather_rows(pr.arena.theta).cpu()
+        if ctx.is_main:
+            solo = DistContext.single(ctx.device)
+            pr1 = build_problem(solo, _cycle(n_nodes), oc, 10 ** 9, samples_per_node=640)
+            opt1 = build_optimizer(pr1, solo.device, copy.deepcopy(oc))
+            opt1.run_rounds(R)
+            torch.cuda.synchronize()
+            ref = pr1.arena.theta.cpu()
+            rel = ((theta - ref).norm() / ref.norm()).item()
+            detail[alg] = rel
+            worst = max(worst, rel)
+            del opt1, pr1
+        ctx.barrier()
+        del opt, pr
+    return {"status": "pass" if worst < 1e-4 else "fail", "max_rel": worst, "rounds": R, "nodes": n_nodes, "per_alg": detail}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from nn_distributed_training_b200.parallel.context import DistContext
+
+    ctx = DistContext.from_env(use_cuda=True)
+    assert ctx.world_size == args.gpus, f"launched with WORLD_SIZE={ctx.world_size} but --gpus {args.gpus}"
+    dev = ctx.device
+    h = Harness(ctx)
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()                       # thread + NVML handle exist before any barrier of a timed region
+    main = measure_headline(h, ctx, args, args.dtype, sampler, probe=args.extras)
+    clocks = sampler.stop()
+    extra = {"top1_after_rounds": main["top1_after_rounds"], "rounds_done": main["rounds_done"]}
+    if "fixed_cost_probe" in main:
+        extra["fixed_cost_probe"] = main["fixed_cost_probe"]
+    if args.extras:
+        other = "fp32" if args.dtype == "fp64" else "fp64"
+        try:
+            o = measure_headline(h, ctx, args, other)
+            extra[other] = {"value": o["value"], "ms_per_step": o["ms_per_step"], "e2e": o["e2e"], "dtype": other,
+                            "fwd_bwd_kernel": o["fwd_bwd_kernel"], "gpu_launches": o["launches"],
+                            "top1_after_rounds": o["top1_after_rounds"]}
+        except Exception as e:  # noqa: BLE001
+            extra[other] = {"error": repr(e)[:300]}
+        if args.gpus > 1:
+            try:
+                extra["multi_gpu_selfcheck"] = selfcheck(ctx, args)
+            except Exception as e:  # noqa: BLE001
+                extra["multi_gpu_selfcheck"] = {"status": "error", "error": repr(e)[:300]}
+            try:
+                extra["one_per_gpu"] = measure_one_per_gpu(h, ctx, args)
+            except Exception as e:  # noqa: BLE001
+                extra["one_per_gpu"] = {"error": repr(e)[:300]}
     if ctx.is_main:
+        K = args.steps
+        cfg = headline_config(args.gpus)
         out = {
-            "metric": "consensus node-rounds/sec (DiNNO, dist_mnist_PAPER; rounds/sec x graph nodes)",
-            "value": n_nodes * K / (ms / 1e3), "unit": "node-rounds/s", "n_gpus": args.gpus, "steps": K,
-            "warmup": max(W, 3) + n_warm * K, "ms_per_step": ms / K, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "impl": "ours",
-            "config": {"model": "MNISTConvNet(3,5,64) 28440 params", "yaml": "dist_mnist_PAPER.yaml/problem1 (DiNNO)",
-                       "graph": f"cycle, {n_nodes} nodes ({NODES_PER_GPU} per GPU)", "global_batch": BATCH * n_nodes,
-                       "primal_iterations": PITS, "seq_len": None, "parallelism": f"consensus graph, {NODES_PER_GPU} nodes/GPU x {args.gpus} GPU",
-                       "rounds_per_sec": K / (ms / 1e3), "eval": "excluded from timed region", "kernels": round_kernel,
-                       "l2": f"inputs {NODES_PER_GPU * SAMPLES_PER_NODE * 784 / 1e6:.0f} MB/GPU > L2: every round's rows are gathered at random from the HBM-resident shards (never re-used within {SAMPLES_PER_NODE // BATCH} steps); no flush",
-                       "input_pipeline": opt_pipeline,
-                       "compute": "fp32 CUDA-core fused fwd/bwd + fused consensus kernels (reference runs fp64)",
-                       "exchange": f"in-kernel P2P pulls of neighbor rows ({symm_how} peer mapping); no NCCL on the hot path"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-            "extra": {"top1_after_rounds": acc, "rounds_done": rounds_done},
+            "metric": METRIC, "value": main["value"], "unit": "node-rounds/s", "n_gpus": args.gpus, "steps": K,
+            "warmup": max(args.warmup, 3), "ms_per_step": main["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "impl": "ours",
+            "config": cfg, "clocks": clocks, "e2e": main["e2e"], "gpu_launches": main["launches"],
+            "multi_gpu_selfcheck": extra.get("multi_gpu_selfcheck", {}).get("status", "n/a (1 GPU)" if args.gpus == 1 else "skipped"),
+            "details": {"rounds_per_sec": K / (main["ms_per_step"] * K / 1e3), "fwd_bwd_kernel": main["fwd_bwd_kernel"],
+                        "input_pipeline": main["pipeline"], "exchange": f"in-kernel P2P pulls of neighbor rows ({main['symm']} peer mapping, "
+                        f"{main['flags']} flags); no NCCL on the hot path",
+                        "timing": "W warm-up rounds; graphs of the K timed rounds captured beforehand; device rank barrier + host gate; "
+                                  "CUDA events, max over ranks",
+                        "l2": f"inputs {NODES_PER_GPU * SAMPLES_PER_NODE * 784 / 1e6:.0f} MB/GPU > L2: every round's rows are gathered at "
+                              f"random from the HBM-resident shards (never re-used within {SAMPLES_PER_NODE // BATCH} steps); no flush"},
+            "extra": extra,
         }
         print(json.dumps(out))
     if dist.is_initialized():
@@ -289,33 +459,8 @@ def run_ours(args):
 
 # ----------------------------------------------------------- NCCL baseline ----
 def run_nccl_baseline(args):
-    """'The NCCL baseline' of SURVEY §0(ii): the same update rules as plain PyTorch — autograd/cuDNN
-    forward+backward per node, NCCL all_gather of the parameter rows, torch ops for mixing and Adam —
-    one rank per GPU, fp32.  This is the path a solution that 'only calls NCCL' would be."""
-    import torch
-    import torch.distributed as dist
-    from nn_distributed_training_b200.optimizers import DiNNO
-    from nn_distributed_training_b200.parallel.context import DistContext
-
-    ctx = DistContext.from_env(use_cuda=True)
-    n_nodes = NODES_PER_GPU * args.gpus
-    W, K = args.warmup, args.steps
-    oc = dict(opt_conf(max(PAPER_ROUNDS, W + K + 1)), consensus_backend="torch")
-    pr = build_problem(ctx, n_nodes, oc, 10 ** 9, extra={"backend": "torch"}, samples_per_node=REF_SAMPLES_PER_NODE, backend="torch")
-    opt = DiNNO(pr, ctx.device, oc)
-    opt.run_rounds(W)
-    torch.cuda.synchronize(); ctx.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); opt.run_rounds(K); e1.record(); torch.cuda.synchronize(); ctx.barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=ctx.device)
-    ms = float(ctx.all_reduce_max(t).item())
-    if ctx.is_main:
-        print(json.dumps({"metric": "consensus node-rounds/sec (DiNNO, dist_mnist_PAPER; rounds/sec x graph nodes)",
-                          "impl": "nccl_baseline (PyTorch eager + NCCL all_gather, this repo's torch path)", "value": n_nodes * K / (ms / 1e3),
-                          "unit": "node-rounds/s", "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": ms / K,
-                          "dtype": "fp32", "data": "synthetic", "higher_is_better": True, "scaling": "weak"}))
-    if dist.is_initialized():
-        dist.destroy_process_group()
+    from baseline.nccl_baseline import run as run_nccl
+    run_nccl(args, METRIC, NODES_PER_GPU, BATCH, PITS, opt_conf, _shard)
 
 
 # --------------------------------------------------------------- reference ----
@@ -346,7 +491,14 @@ def run_reference(args):
         import contextlib
         try:
             with contextlib.redirect_stdout(sys.stderr):      # the reference prints its metrics; stdout carries one JSON line
-                out = _reference_rank0(args, ref)
+                out = _reference_rank0(args, ref, args.dtype, REF_MAX_SECONDS * (0.6 if args.extras else 1.0))
+                if args.extras:
+                    other = "fp32" if args.dtype == "fp64" else "fp64"
+                    try:
+                        o = _reference_rank0(args, ref, other, REF_MAX_SECONDS * 0.4)
+                        out["extra"] = {other: {"value": o["value"], "ms_per_step": o["ms_per_step"], "steps": o["steps"], "dtype": other}}
+                    except Exception as e:  # noqa: BLE001
+                        out["extra"] = {other: {"error": repr(e)[:200]}}
         except Exception as e:  # noqa: BLE001
             out = {"impl": "reference", "unavailable": "reference run failed: " + repr(e)[:200]}
         print(json.dumps(out), flush=True)
@@ -355,16 +507,18 @@ def run_reference(args):
         dist.destroy_process_group()
 
 
-def _reference_rank0(args, ref):
-    import numpy as np
+def _reference_rank0(args, ref, dtype, budget_s):
     import torch
-    sys.path.insert(0, ref)
-    torch.set_default_dtype(torch.float64)   # what the stock runner does on import (experiments/dist_mnist_ex.py:19)
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    # float64 is what the stock runner sets on import (experiments/dist_mnist_ex.py:19); the fp32 run uses the same
+    # unmodified classes with the other default dtype
+    torch.set_default_dtype(torch.float64 if dtype == "fp64" else torch.float32)
     from models.mnist_conv_nn import MNISTConvNet
     from optimizers.dinno import DiNNO
     from problems.dist_mnist_problem import DistMNISTProblem
     from utils import graph_generation
-    from nn_distributed_training_b200.data.mnist import synthetic_mnist, MNIST_MEAN, MNIST_STD
+    from nn_distributed_training_b200.data.mnist import MNIST_MEAN, MNIST_STD
 
     class U8Images(torch.utils.data.Dataset):
         """uint8 images -> normalised default-dtype tensors per item (the job torchvision's
@@ -380,15 +534,15 @@ def _reference_rank0(args, ref):
             return ((self.x[i].to(torch.get_default_dtype()) / 255.0) - MNIST_MEAN) / MNIST_STD, int(self.y[i])
 
     n_nodes = NODES_PER_GPU * args.gpus
-    W, K_req = args.warmup, args.steps
+    W, K_req = max(args.warmup, 3), args.steps
     # The stock path simulates every node sequentially (measured 4.65 ms per node-round on B200): bound the timed
-    # region to ~REF_MAX_SECONDS so `--gpus 8 --steps 1000` (6 minutes of reference rounds) cannot time the driver out.
+    # region so `--gpus 8 --steps 1000` (6 minutes of reference rounds) cannot time the driver out.
     # The JSON reports the steps actually timed.
-    K = min(K_req, max(5, int(REF_MAX_SECONDS / (REF_SEC_PER_NODE_ROUND * n_nodes))))
+    K = min(K_req, max(5, int(budget_s / (REF_SEC_PER_NODE_ROUND * n_nodes)) - W))
     device = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
     N, graph = graph_generation.generate_from_conf({"num_nodes": n_nodes, "type": "cycle", "p": 0.3, "gen_attempts": 100})
-    train = [U8Images(synthetic_mnist(REF_SAMPLES_PER_NODE, seed=100 + g, classes=[g % 10])) for g in range(N)]
-    val = U8Images(synthetic_mnist(10000, seed=1))
+    train = [U8Images(_shard(REF_SAMPLES_PER_NODE, 100 + g, [g % 10])) for g in range(N)]
+    val = U8Images(_shard(10000, 1, None))
     torch.manual_seed(0)
     base = MNISTConvNet(3, 5, 64)
     oc = opt_conf(W + K + 1)
@@ -396,33 +550,39 @@ def _reference_rank0(args, ref):
     prob = DistMNISTProblem(graph, base, torch.nn.NLLLoss(), train, val, device, pc)
     dopt = DiNNO(prob, device, oc)
     sampler = ClockSampler(0)
-    timer = StepTimer(W, K, on_start=sampler.start)
+    sampler.start()
+
+    def on():
+        sampler.active = True
+
+    timer = StepTimer(W, K, on_start=on)
     dopt.train(profiler=timer)     # evaluates at k=0 (before warm-up) and at the last, untimed, round
     clocks = sampler.stop()
     ms = timer.ms()
-    h2d = N * PITS * BATCH * (784 * 8 + 8)
-    out = {"metric": "consensus node-rounds/sec (DiNNO, dist_mnist_PAPER; rounds/sec x graph nodes)",
-           "value": N * K / (ms / 1e3), "unit": "node-rounds/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
+    itemsize = 8 if dtype == "fp64" else 4
+    h2d = N * PITS * BATCH * (784 * itemsize + 8)
+    out = {"metric": METRIC, "value": N * K / (ms / 1e3), "unit": "node-rounds/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "fp64", "data": "synthetic", "impl": "reference", "steps_requested": K_req,
-           "config": {"model": "MNISTConvNet(3,5,64) 28440 params", "yaml": "dist_mnist_PAPER.yaml/problem1 (DiNNO)",
-                      "graph": f"cycle, {N} nodes (all simulated on one device: the reference's only mode)",
-                      "global_batch": BATCH * N, "primal_iterations": PITS, "seq_len": None,
-                      "parallelism": "single process, single device", "rounds_per_sec": K / (ms / 1e3),
-                      "eval": "excluded from timed region", "l2": "inputs streamed from host memory every step"},
+           "dtype": dtype, "data": "synthetic", "impl": "reference", "steps_requested": K_req,
+           "config": headline_config(args.gpus),
            "clocks": clocks,
            "e2e": {"value": N * K / (ms / 1e3), "unit": "node-rounds/s", "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": 0, "note": "stock path already feeds every batch from host memory"},
-           "gpu_launches": None}
+           "gpu_launches": None,
+           "details": {"rounds_per_sec": K / (ms / 1e3), "graph": f"cycle, {N} nodes, all simulated on one device: the reference's only mode",
+                       "parallelism": "single process, single device", "l2": "inputs streamed from host memory every step"}}
     return out
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl"])
+    ap.add_argument("--dtype", default=os.environ.get("NNDT_BENCH_DTYPE", "fp64"), choices=["fp64", "fp32"])
+    ap.add_argument("--no-extras", dest="extras", action="store_false",
+                    help="headline only: skip the other-precision run, the one-node-per-GPU sweep, the self-check and the probe")
     args = ap.parse_args()
     if args.impl == "reference":
         if "--steps" not in " ".join(sys.argv):

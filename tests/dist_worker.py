@@ -41,17 +41,74 @@ def build(ctx, N, graph, conf, backend, M=200, pipeline="resident"):
                             backend=backend, seed=11)
 
 
+def delayed(ctx, N, G, backend):
+    """Buffer-reuse protocol under stress: the graph changes EVERY round (fault-injected link drops),
+    every neighbor read is checked against its round tag (debug_sequence_check), rounds are launched one at a time and one
+    rank is held back by a spin kernel before every other round, so its peers run ahead as far as the protocol lets them.
+    The gathered parameters must equal the single-process run."""
+    from nn_distributed_training_b200.ops import load_ext
+    ext = load_ext(required=True)
+    ok = True
+    R = 14
+    for alg in ("dinno", "dsgd", "dsgt"):
+        conf = dict(copy.deepcopy(CONFS[alg]), outer_iterations=R, debug_sequence_check=True)
+        extra = {"fault_injection": {"link_drop_prob": 0.45, "seed": 3, "from_round": 0, "to_round": R}}
+
+        def make(c):
+            data = synthetic_mnist(200 * N, seed=3)
+            val = synthetic_mnist(128, seed=4)
+            shards = [data.select(torch.arange(i * 200, (i + 1) * 200)) for i in range(N)]
+            pconf = {"problem_name": "t", "train_batch_size": 32, "val_batch_size": 64, "metrics": METRICS,
+                     "metrics_config": {"evaluate_frequency": 10 ** 6}, "optimizer_config": conf, **extra}
+            torch.manual_seed(5)
+            return DistMNISTProblem(G, MNISTConvNet(3, 5, 64), torch.nn.NLLLoss(), shards, val, c.device, pconf, ctx=c,
+                                    backend=backend, seed=11)
+        pr = make(ctx)
+        opt = build_optimizer(pr, ctx.device, copy.deepcopy(conf))
+        slow = ctx.world_size - 1
+        for r in range(R):
+            if ctx.rank == slow and r % 2 == 1:
+                ext.spin(600_000)            # ~0.3 ms: many round times
+            if ctx.rank == 0 and r % 3 == 2:
+                ext.spin(300_000)
+            opt.run_rounds(1)
+        torch.cuda.synchronize()
+        opt._program.eng.check()             # raises on a stale tag (err == 2) or a spin timeout
+        ngraphs = len(opt._program.eng.topos)
+        theta = pr.gather_rows(pr.arena.theta).cpu()
+        if ctx.is_main:
+            solo = DistContext.single(ctx.device)
+            pr1 = make(solo)
+            opt1 = build_optimizer(pr1, solo.device, copy.deepcopy(conf))
+            opt1.run_rounds(R)
+            torch.cuda.synchronize()
+            ref = pr1.arena.theta.cpu()
+            rel = ((theta - ref).norm() / ref.norm()).item()
+            good = rel < 1e-5
+            print(f"[delayed] {alg} world={ctx.world_size} distinct_graphs={ngraphs} rel={rel:.2e} {'OK' if good else 'MISMATCH'}", flush=True)
+            ok = ok and good and ngraphs > 3
+        ctx.barrier()
+    if ctx.is_main:
+        print("DIST_RESULT", "PASS" if ok else "FAIL", flush=True)
+    if torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cuda", type=int, default=0)
     ap.add_argument("--nodes", type=int, default=6)
     ap.add_argument("--graph", default="cycle")
     ap.add_argument("--pipeline", default="resident")   # host: device-initiated staging + forked peer announcement
+    ap.add_argument("--delayed", type=int, default=0)   # 1: time-varying graphs (link drops) + a deliberately slow rank
     args = ap.parse_args()
     ctx = DistContext.from_env(use_cuda=bool(args.cuda))
     N = args.nodes
     G = {"cycle": nx.cycle_graph(N), "wheel": nx.wheel_graph(N), "complete": nx.complete_graph(N)}[args.graph]
     backend = "fused" if args.cuda else "torch"
+    if args.delayed:
+        return delayed(ctx, N, G, backend)
     ok = True
     for alg, conf in CONFS.items():
         if args.pipeline == "host" and alg == "dsgt":

@@ -52,7 +52,7 @@ def test_reference_arm_runs_the_unmodified_reference(monkeypatch):
     dtype = torch.get_default_dtype()
     try:
         with contextlib.redirect_stdout(sys.stderr):
-            out = bench._reference_rank0(types.SimpleNamespace(gpus=1, warmup=1, steps=2), ref)
+            out = bench._reference_rank0(types.SimpleNamespace(gpus=1, warmup=3, steps=2, extras=False), ref, "fp64", 60.0)
     finally:
         torch.set_default_dtype(dtype)            # the stock runner switches the process to float64
         for m in [k for k in sys.modules if k.split(".")[0] in ("models", "optimizers", "problems", "utils")]:
@@ -65,11 +65,13 @@ def test_reference_arm_runs_the_unmodified_reference(monkeypatch):
         assert key in line, key
     assert line["impl"] == "reference" and line["steps"] == 2 and line["dtype"] == "fp64" and line["value"] > 0
     assert line["e2e"]["h2d_bytes_per_step"] > 0
+    # both arms print the same config dict (the driver compares them)
+    assert line["config"] == bench.headline_config(1)
 
 
 def test_reference_arm_caps_the_timed_region():
     import bench
     # 8 "GPUs" x 10 nodes at 4.65 ms per node-round: 1000 requested rounds would take 6 minutes
     n_nodes = bench.NODES_PER_GPU * 8
-    k = min(1000, max(5, int(bench.REF_MAX_SECONDS / (bench.REF_SEC_PER_NODE_ROUND * n_nodes))))
+    k = min(1000, max(5, int(bench.REF_MAX_SECONDS / (bench.REF_SEC_PER_NODE_ROUND * n_nodes)) - 5))
     assert 100 < k < 1000 and k * bench.REF_SEC_PER_NODE_ROUND * n_nodes <= bench.REF_MAX_SECONDS

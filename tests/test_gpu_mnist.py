@@ -280,3 +280,73 @@ def test_fused_link_drop_fault_injection_matches_torch_ops(cls, conf):
             assert len(opt._program.eng.topos) > 2            # several distinct faulted graphs were tabulated
             opt._program.eng.check()
     _assert_mostly_close(outs[0], outs[1])
+
+
+# ---- generic conv-net kernel (csrc/mnist_generic.cu): every MNISTConvNet shape, fp32 and fp64 ---------------------
+def _generic_problem(shape, dtype, backend, B=32, N=3, M=150, eval_every=1000, conf=None):
+    torch.manual_seed(0)
+    data = synthetic_mnist(M * N, seed=3)
+    val = synthetic_mnist(200, seed=4)
+    shards = [data.select(torch.arange(i * M, (i + 1) * M)) for i in range(N)]
+    conf = conf or {"alg_name": "dsgd", "alpha0": 0.01, "mu": 0.001, "outer_iterations": 2, "profile": False}
+    pconf = {"problem_name": "t", "train_batch_size": B, "val_batch_size": 64, "metrics": METRICS,
+             "metrics_config": {"evaluate_frequency": eval_every}, "optimizer_config": conf}
+    model = MNISTConvNet(*shape)
+    if dtype == torch.float64:
+        model = model.double()
+    return DistMNISTProblem(nx.cycle_graph(N), model, torch.nn.NLLLoss(), shards, val, DEV, pconf, backend=backend, seed=7)
+
+
+@pytest.mark.parametrize("shape,dtype,B", [((3, 5, 64), torch.float64, 64), ((3, 5, 64), torch.float64, 37),
+                                           ((8, 3, 128), torch.float64, 32), ((8, 3, 128), torch.float32, 32),
+                                           ((2, 5, 32), torch.float32, 24), ((4, 3, 64), torch.float64, 16),
+                                           ((6, 5, 128), torch.float32, 64)])
+def test_generic_convnet_kernel_matches_autograd(shape, dtype, B):
+    fused = _generic_problem(shape, dtype, "fused", B=B)
+    ref = _generic_problem(shape, dtype, "torch", B=B)
+    assert fused.backend == "fused" and fused.fused.generic and ref.backend == "torch"
+    ref.arena.theta.copy_(fused.arena.theta)
+    for step in range(4):
+        lf = fused.compute_grads().clone()
+        lr = ref.compute_grads().clone()
+        if dtype == torch.float64:
+            torch.testing.assert_close(lf, lr, rtol=1e-6, atol=1e-7)      # loss partials are stored as float
+            torch.testing.assert_close(fused.arena.grad, ref.arena.grad, rtol=1e-9, atol=1e-11)
+        else:
+            torch.testing.assert_close(lf, lr, rtol=2e-4, atol=2e-5)
+            _assert_grads_close(fused.arena.grad, ref.arena.grad)
+    pf, of = fused._validate_local()
+    prf, orf = ref._validate_local()
+    if dtype == torch.float64:
+        torch.testing.assert_close(pf, prf, rtol=1e-9, atol=1e-11)
+        assert (of == orf).all()
+    else:
+        torch.testing.assert_close(pf, prf, rtol=2e-4, atol=2e-5)
+
+
+def test_generic_kernel_env_switch_on_paper_shape_fp32(monkeypatch):
+    """NNDT_MNIST_GENERIC=1 routes the paper shape through the generic kernel too (A/B switch); same gradients."""
+    monkeypatch.setenv("NNDT_MNIST_GENERIC", "1")
+    fused = _generic_problem((3, 5, 64), torch.float32, "fused", B=64)
+    monkeypatch.delenv("NNDT_MNIST_GENERIC")
+    spec = _generic_problem((3, 5, 64), torch.float32, "fused", B=64)
+    assert fused.fused.generic and not spec.fused.generic
+    spec.arena.theta.copy_(fused.arena.theta)
+    fused.compute_grads(); spec.compute_grads()
+    _assert_grads_close(fused.arena.grad, spec.arena.grad)
+
+
+@pytest.mark.parametrize("cls,conf", [(DiNNO, DINNO), (DSGD, DSGD_C), (DSGT, DSGT_C)])
+def test_fp64_fused_training_matches_torch_fp64(cls, conf):
+    """The float64 arm (bench headline): fused fp64 forward/backward + fp64 consensus kernels under CUDA graphs against
+    autograd + the PyTorch consensus ops in float64 — agreement to fp64 round-off, not fp32."""
+    a = _generic_problem((3, 5, 64), torch.float64, "fused", B=32, N=5, eval_every=3, conf=copy.deepcopy(conf))
+    b = _generic_problem((3, 5, 64), torch.float64, "torch", B=32, N=5, eval_every=3, conf=copy.deepcopy(conf))
+    b.arena.theta.copy_(a.arena.theta)
+    oa = cls(a, DEV, copy.deepcopy(conf))
+    ob = cls(b, DEV, dict(copy.deepcopy(conf), consensus_backend="torch"))
+    oa.train()
+    ob.train()
+    rel = ((a.arena.theta - b.arena.theta).norm() / b.arena.theta.norm()).item()
+    assert rel < 1e-8, rel
+    assert a.forward_cnt == b.forward_cnt
