@@ -3,6 +3,8 @@
 // PyTorch's current CUDA stream, so they compose with torch.cuda.graph capture: a whole
 // consensus round is captured once and replayed.
 #include <torch/extension.h>
+#include <cstring>
+#include <string>
 #include <ATen/cuda/CUDAContext.h>
 #include <pybind11/pybind11.h>
 
@@ -28,7 +30,8 @@ static double getf(const py::dict& d, const char* k, double dflt = 0) { return d
 struct MnistOp {
   mnist::Args a{};
   mnist::GenericShape gs{3, 5, 64, 0};
-  int spb = 8, S = 1, eval_ctas = 1, generic = 0;
+  int spb = 8, S = 1, eval_ctas = 1, generic = 0, tc = 0;
+  alignas(64) unsigned char w1_map[128] = {0};
   explicit MnistOp(const py::dict& d) { update(d); }
   void update(const py::dict& d) {
     a.theta = ptr<const float>(d, "theta"); a.n_pad = geti(d, "n_pad"); a.L = geti(d, "L");
@@ -47,9 +50,17 @@ struct MnistOp {
     generic = geti(d, "generic", 0);
     gs.F = geti(d, "num_filters", 3); gs.KS = geti(d, "kernel_size", 5); gs.LW = geti(d, "linear_width", 64);
     gs.dtype64 = geti(d, "dtype64", 0);
+    // tcgen05 K-split cluster kernel (mnist_tc.cu): needs the W1 tensor map
+    tc = geti(d, "tc", 0);
+    if (tc) {
+      const std::string m = d["w1_map"].cast<py::bytes>();
+      if (m.size() != 128) throw std::runtime_error("w1_map must be the 128-byte CUtensorMap");
+      memcpy(w1_map, m.data(), 128);
+    }
   }
   void train() {
     if (generic) check(mnist::launch_generic_train(a, gs, spb, S, cur_stream()), "convnet_generic_train");
+    else if (tc) check(mnist::launch_train_tc(a, w1_map, cur_stream()), "mnist_tc_train");
     else check(mnist::launch_train(a, spb, S, cur_stream()), "mnist_train");
   }
   void eval() {
@@ -185,6 +196,12 @@ PYBIND11_MODULE(_C, m) {
   m.def("convnet_generic_smem_bytes", [](int F, int KS, int LW, int dtype64, int spb) {
     return (size_t)mnist::generic_smem_bytes(mnist::GenericShape{F, KS, LW, dtype64}, dtype64, spb);
   });
+  m.def("make_w1_tensor_map", [](uint64_t theta, int n_pad, int L, int off_w1) {
+    unsigned char buf[128];
+    check(mnist::make_w1_tensor_map(reinterpret_cast<const float*>(theta), n_pad, L, off_w1, buf), "make_w1_tensor_map");
+    return py::bytes(reinterpret_cast<const char*>(buf), 128);
+  });
+  m.def("mnist_tc_max_clusters", []() { return mnist::tc_max_active_clusters(); });
   m.def("rank_barrier", [](uint64_t slots, uint64_t peer_slot, int world, int rank, int epoch, uint64_t gate, uint64_t err) {
     check(consensus::launch_rank_barrier(reinterpret_cast<int*>(slots), reinterpret_cast<const int64_t*>(peer_slot), world, rank,
                                          epoch, reinterpret_cast<const volatile int*>(gate), reinterpret_cast<int*>(err), cur_stream()),

@@ -51,6 +51,14 @@ class FusedMnist:
                         or choose_spb(self.B, self.L, sms))
             assert 4 <= self.spb <= SPB
         self.S = -(-self.B // self.spb)
+        # paper shape, fp32, batch <= 64: the tcgen05 / TMEM K-split cluster kernel (csrc/mnist_tc.cu) — one gradient
+        # row per node instead of S per-slice partials.  NNDT_MNIST_TC=0 keeps the batch-split mma.sync kernel (A/B).
+        self.tc = (not self.generic and self.B <= 64 and os.environ.get("NNDT_MNIST_TC", "1") != "0"
+                   and str(problem.conf.get("mnist_kernel", "tc")) == "tc" and self.ext.mnist_tc_max_clusters() >= 1)
+        if self.tc:
+            self.S = 1
+        self.kernel_name = ("mnist_tc_train_kernel (tcgen05 kind::tf32 3xTF32, TMEM, TMA tensor map, 6-CTA cluster per node)" if self.tc
+                            else "convnet_generic_kernel (CUDA cores)" if self.generic else "mnist_kernel (mma.sync 3xTF32)")
         sh = problem.shards
         self.x = sh.x.reshape(sh.x.shape[0], -1).contiguous()
         assert self.x.shape[1] == 784
@@ -81,6 +89,8 @@ class FusedMnist:
             spb=self.spb, S=self.S, tune=int(os.environ.get("NNDT_MNIST_TUNE", "1")),
             generic=int(self.generic), num_filters=spec.num_filters, kernel_size=spec.kernel_size,
             linear_width=spec.linear_width, dtype64=int(self.dtype == torch.float64))
+        if self.tc:
+            self.base.update(tc=1, w1_map=self.ext.make_w1_tensor_map(a.theta.data_ptr(), a.n_pad, self.L, off[names[2]]))
         if os.environ.get("NNDT_STEP_PROF") == "1":     # scripts/profile_round_phases.py --per-step
             self.step_prof = torch.zeros(self.L * self.S, 64, dtype=torch.int64, device=dev)
             self.base["step_prof"] = self.step_prof.data_ptr()
@@ -99,7 +109,7 @@ class FusedMnist:
 
     def supports_round_kernel(self, opt) -> bool:
         """The cluster kernel needs the node's S batch slices in one cluster (S <= 8 CTAs) and fp32 state."""
-        return (not self.generic and opt.alg_name == "dinno" and self.spb == SPB and self.S <= 8 and 1 <= opt.pits <= self.MAX_ROUND_STEPS
+        return (not self.generic and not self.tc and opt.alg_name == "dinno" and self.spb == SPB and self.S <= 8 and 1 <= opt.pits <= self.MAX_ROUND_STEPS
                 and self.pr.arena.dtype == torch.float32 and self.ext.dinno_round_max_clusters(self.S) >= 1)
 
     def round_op(self, cons_dict, stage_set=None):
@@ -212,7 +222,8 @@ class FusedMnist:
         # a training CTA fills an SM's register file (768 threads x 80 registers): a staging block that lands on
         # an SM evicts a training CTA into a second wave, so the staging grid is sized to the SMs left over
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        free = sms - self.L * self.S if self.L * self.S <= sms else 0      # multi-wave grids leave no SM idle
+        ctas = self.L * (6 if self.tc else self.S)
+        free = sms - ctas if ctas <= sms else 0      # multi-wave grids leave no SM idle
         gather_blocks = int(os.environ.get("NNDT_GATHER_BLOCKS", "0")) or max(8, min(24, free - 2))
         self.direct_ops, self.gather_ops = [], []
         for b in range(2):

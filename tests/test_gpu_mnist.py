@@ -350,3 +350,28 @@ def test_fp64_fused_training_matches_torch_fp64(cls, conf):
     rel = ((a.arena.theta - b.arena.theta).norm() / b.arena.theta.norm()).item()
     assert rel < 1e-8, rel
     assert a.forward_cnt == b.forward_cnt
+
+
+# ---- tcgen05 K-split cluster kernel (csrc/mnist_tc.cu) ------------------------------------------------------------
+@pytest.mark.parametrize("B,float_inputs", [(64, False), (37, False), (64, True), (8, False)])
+def test_tc_kernel_matches_batch_split_kernel_and_autograd(B, float_inputs, monkeypatch):
+    """The tensor-core kernel (default for the paper shape at batch <= 64) against the mma.sync batch-split kernel
+    (NNDT_MNIST_TC=0) and against PyTorch autograd: 3xTF32 keeps fp32-level agreement."""
+    conf = {"alg_name": "dsgd", "alpha0": 0.01, "mu": 0.001, "outer_iterations": 2, "profile": False}
+    tc = _problem(3, B, "fused", conf, M=150, float_inputs=float_inputs)
+    monkeypatch.setenv("NNDT_MNIST_TC", "0")
+    old = _problem(3, B, "fused", conf, M=150, float_inputs=float_inputs)
+    monkeypatch.delenv("NNDT_MNIST_TC")
+    ref = _problem(3, B, "torch", conf, M=150, float_inputs=float_inputs)
+    assert tc.fused.tc and tc.fused.S == 1 and not old.fused.tc
+    old.arena.theta.copy_(tc.arena.theta)
+    ref.arena.theta.copy_(tc.arena.theta)
+    for step in range(4):
+        lt = tc.compute_grads().clone()
+        lo = old.compute_grads().clone()
+        lr = ref.compute_grads().clone()
+        torch.testing.assert_close(lt, lr, rtol=2e-4, atol=2e-5)
+        torch.testing.assert_close(lt, lo, rtol=2e-4, atol=2e-5)
+        _assert_grads_close(tc.arena.grad, ref.arena.grad)
+        _assert_grads_close(tc.arena.grad, old.arena.grad)
+    assert (tc.calls == ref.calls).all()
