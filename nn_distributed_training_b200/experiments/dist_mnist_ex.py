@@ -77,8 +77,8 @@ def experiment(yaml_pth):
     if exp_conf["writeout"] and ctx.is_main:
         common.write_gpickle(graph, os.path.join(output_dir, "graph.gpickle"))
 
-    train, src = load_mnist(exp_conf["data_dir"], train=True)
-    val, _ = load_mnist(exp_conf["data_dir"], train=False)
+    train, src = load_mnist(exp_conf["data_dir"], train=True, source=exp_conf.get("data_source", "auto"))
+    val, _ = load_mnist(exp_conf["data_dir"], train=False, source=exp_conf.get("data_source", "auto"))
     if ctx.is_main:
         print(f"MNIST source: {src} ({len(train)} train / {len(val)} val)")
     if exp_conf["data_split_type"] == "random":
@@ -108,6 +108,7 @@ def experiment(yaml_pth):
     for prob_key, prob_conf in conf_dict["problem_configs"].items():
         prob = DistMNISTProblem(graph, base_model, base_loss, train_subsets, val, ctx.device, prob_conf,
                                 ctx=ctx, seed=int(exp_conf.get("seed", 0)))
+        prob.data_source = src          # stored in <problem>_results.pt: synthetic runs stay distinguishable from MNIST runs
         common.run_problem(prob, prob_conf, exp_conf, ctx)
     return conf_dict
 

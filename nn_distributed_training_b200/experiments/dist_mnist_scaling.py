@@ -38,8 +38,8 @@ def experiment(yaml_pth):
     exp_conf = conf_dict["experiment"]
     ctx = common.make_context(exp_conf)
     output_dir = common.setup_output(exp_conf, yaml_pth, ctx)
-    train, src = load_mnist(exp_conf["data_dir"], train=True)
-    val, _ = load_mnist(exp_conf["data_dir"], train=False)
+    train, src = load_mnist(exp_conf["data_dir"], train=True, source=exp_conf.get("data_source", "auto"))
+    val, _ = load_mnist(exp_conf["data_dir"], train=False, source=exp_conf.get("data_source", "auto"))
     model_conf = exp_conf["model"]
     torch.manual_seed(int(exp_conf.get("seed", 0)))
     base_model = MNISTConvNet(model_conf["num_filters"], model_conf["kernel_size"], model_conf["linear_width"])

@@ -76,9 +76,18 @@ class DSGT(ConsensusOptimizer):
         grads = torch.autograd.grad(loss, list(pr.models[i].parameters()))
         pr.arena.set_row_from_grads(i, grads)
 
+    def _use_engine(self) -> bool:
+        # the fused dsgt_mix kernel implements theta_i <- sum_j W_ij (theta_j - alpha y_j) with a scalar alpha: the RL
+        # variant (own tracker, un-mixed) and per-coordinate step sizes stay on the PyTorch ops instead of being
+        # silently ignored
+        if self.own_tracker_step or torch.is_tensor(self.alpha):
+            return False
+        return super()._use_engine()
+
     def state_dict(self) -> Dict:
         sd = super().state_dict()
-        sd.update(y=self.y.cpu().clone(), g=self.g.cpu().clone(), initialised=self._initialised)
+        sd.update(y=self.y.cpu().clone(), g=self.g.cpu().clone(), initialised=self._initialised,
+                  alpha=self.alpha.detach().cpu().clone() if torch.is_tensor(self.alpha) else float(self.alpha))
         return sd
 
     def load_state_dict(self, sd: Dict):
@@ -86,3 +95,5 @@ class DSGT(ConsensusOptimizer):
         self.y.copy_(sd["y"].to(self.device))
         self.g.copy_(sd["g"].to(self.device))
         self._initialised = bool(sd["initialised"])
+        if "alpha" in sd:
+            self.alpha = sd["alpha"].to(self.device) if torch.is_tensor(sd["alpha"]) else float(sd["alpha"])

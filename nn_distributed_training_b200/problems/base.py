@@ -252,7 +252,10 @@ class ConsensusProblem:
         if not self.ctx.is_main:
             return
         path = os.path.join(output_dir, self.conf["problem_name"] + "_results.pt")
-        torch.save(self.metrics, path)
+        out = dict(self.metrics)
+        if getattr(self, "data_source", None) is not None:
+            out["data_source"] = self.data_source     # extra key next to the reference's metric lists
+        torch.save(out, path)
 
     def state_dicts(self) -> Dict[int, dict]:
         """``{node: state_dict}`` for every node (gathered to all ranks)."""

@@ -25,6 +25,10 @@ class Checkpointer:
         return os.path.join(self.dir, f"{self.name}_ckpt_rank{self.ctx.rank}.pt")
 
     def next_save_after(self, k: int) -> int:
+        """First round > k at which a checkpoint is due (a huge sentinel when periodic saving is off, e.g. a
+        ``resume: true`` run without ``checkpoint_every``)."""
+        if self.every <= 0:
+            return 2 ** 62
         return (k // self.every + 1) * self.every
 
     def maybe_save(self, opt):
@@ -40,7 +44,8 @@ class Checkpointer:
             prog.sync_back()
         payload = {"optimizer": opt.state_dict(), "alg": opt.alg_name,
                    "calls": np.asarray(pr.calls).copy(), "forward_cnt": pr.forward_cnt,
-                   "metrics": pr.metrics, "world_size": self.ctx.world_size}
+                   "metrics": pr.metrics, "world_size": self.ctx.world_size,
+                   "graph_round": int(getattr(pr, "_graph_round", 0))}
         if hasattr(pr, "tloss_local"):
             payload["tloss_local"] = pr.tloss_local.cpu()
         tmp = self.path() + ".tmp"
@@ -62,6 +67,13 @@ class Checkpointer:
         pr.metrics = payload["metrics"]
         if "tloss_local" in payload and hasattr(pr, "tloss_local"):
             pr.tloss_local.copy_(payload["tloss_local"].to(pr.device))
+        if hasattr(pr, "_graph_round"):
+            pr._graph_round = int(payload.get("graph_round", opt.k))     # fault-injection schedule of the PyTorch path
+        # the fused forward/backward kernels sample from DEVICE draw counters: mirror the restored host counters, also when
+        # the consensus ops run on the PyTorch path (RoundProgram does this itself when it is built)
+        fused = getattr(pr, "fused", None)
+        if fused is not None and hasattr(fused, "sync_calls_from_host"):
+            fused.sync_calls_from_host()
         self._last_saved = opt.k
         return True
 
@@ -69,16 +81,30 @@ class Checkpointer:
 def attach(opt, directory: str, name: str, every: int, ctx, resume: bool = False) -> Checkpointer:
     cp = Checkpointer(directory, name, every, ctx)
     opt.checkpointer = cp
-    if resume and cp.load(opt) and ctx.is_main:
-        print(f"resumed {name} at round {opt.k}")
+    if resume:
+        if cp.load(opt):
+            if ctx.is_main:
+                print(f"resumed {name} at round {opt.k} from {cp.path()}")
+        elif ctx.is_main:
+            print(f"[nndt] WARNING: resume requested but no checkpoint at {cp.path()}: starting {name} from round 0", flush=True)
     return cp
 
 
 def attach_from_conf(opt, opt_conf, output_dir: str, name: str, ctx) -> Optional[Checkpointer]:
-    """YAML keys (extensions): ``checkpoint_every`` (rounds, 0 = off), ``checkpoint_dir``
-    (default: the run's output directory), ``resume``."""
+    """YAML keys (extensions): ``checkpoint_every`` (rounds, 0 = off), ``checkpoint_dir``, ``resume``.
+
+    The run's output directory is time-stamped (``<metadir>/<Y-m-d_H-M>_<name>``), so a checkpoint written there cannot
+    be found by a second invocation.  ``checkpoint_dir`` therefore defaults to the STABLE sibling
+    ``<metadir>/<name>_ckpt`` (run name = the part of the output directory after the time stamp): the two-invocation
+    flow is simply "same YAML with ``resume: true``"."""
     every = int(opt_conf.get("checkpoint_every", 0) or 0)
     resume = bool(opt_conf.get("resume", False))
     if every <= 0 and not resume:
         return None
-    return attach(opt, opt_conf.get("checkpoint_dir") or output_dir, name, max(every, 0), ctx, resume=resume)
+    directory = opt_conf.get("checkpoint_dir")
+    if not directory:
+        meta, leaf = os.path.split(os.path.normpath(output_dir))
+        parts = leaf.split("_", 2)          # <date>_<time>_<name>
+        run = parts[2] if len(parts) == 3 else leaf
+        directory = os.path.join(meta, run + "_ckpt")
+    return attach(opt, directory, name, max(every, 0), ctx, resume=resume)

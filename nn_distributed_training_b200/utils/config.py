@@ -140,6 +140,12 @@ def validate_experiment(conf: Dict[str, Any], kind: str) -> Dict[str, Any]:
             raise ConfigError("experiment.data_split_type must be random|hetero")
     if kind == "mnist_scaling":
         exp = _fill(exp, {"data_dir": "../data/", "scaling": REQUIRED}, "experiment")
+    if kind.startswith("mnist"):
+        exp.setdefault("data_source", "auto")
+        if exp["data_source"] not in ("auto", "mnist", "synthetic", "synthetic_hard"):
+            raise ConfigError("experiment.data_source must be auto|mnist|synthetic|synthetic_hard")
+        if exp.get("dtype", "float32") not in ("float32", "float64"):
+            raise ConfigError("experiment.dtype must be float32|float64")
     if kind in ("density", "online_density"):
         exp = _fill(exp, {"data": REQUIRED}, "experiment")
         if kind == "online_density":

@@ -82,8 +82,10 @@ def test_mnist_template_runs_and_writes_reference_layout(tmp_path, monkeypatch):
     files = set(os.listdir(outs[0]))
     assert {"graph.gpickle", "dsgd_results.pt", "dinno_results.pt"} <= files
     assert any(f.endswith(".yaml") for f in files)
-    assert "dinno_ckpt_rank0.pt" in files
+    # checkpoints go to the STABLE sibling <metadir>/<name>_ckpt (the output directory is time-stamped)
+    assert os.path.exists(os.path.join(str(tmp_path), "dist_mnist_template_ckpt", "dinno_ckpt_rank0.pt"))
     res = torch.load(os.path.join(outs[0], "dsgd_results.pt"), weights_only=False)
+    assert res.pop("data_source") == "synthetic"
     assert set(res) == {"forward_pass_count", "validation_loss", "consensus_error", "top1_accuracy", "current_epoch"}
     assert len(res["validation_loss"]) == 4          # rounds 0, 2, 4 and the last (5)
     assert res["validation_loss"][0].shape == (2,)
@@ -92,6 +94,38 @@ def test_mnist_template_runs_and_writes_reference_layout(tmp_path, monkeypatch):
     assert res["forward_pass_count"] == [0, 128, 256, 320]
     from nn_distributed_training_b200.experiments.common import read_gpickle
     assert read_gpickle(os.path.join(outs[0], "graph.gpickle")).number_of_nodes() == 2
+
+
+def test_two_invocation_resume_through_the_yaml_runner(tmp_path, monkeypatch):
+    """`checkpoint_every` in a first invocation, the same YAML with `resume: true` (and no checkpoint_every: the
+    ADVICE r1 ZeroDivisionError case) in a second one: the resumed run continues at the saved round and ends exactly
+    where an uninterrupted run ends."""
+    import nn_distributed_training_b200.data.mnist as M
+    monkeypatch.setattr(M, "load_mnist", lambda d, train, **k: (M.synthetic_mnist(512 if train else 128, seed=int(train)), "synthetic"))
+    monkeypatch.setattr(dist_mnist_ex, "load_mnist", M.load_mnist)
+
+    def run(tag, oits, **extra):
+        conf = _load("dist_mnist_template.yaml")
+        meta = str(tmp_path / tag)
+        os.makedirs(meta, exist_ok=True)
+        conf["experiment"].update(output_metadir=meta, writeout=True)
+        pc = conf["problem_configs"]["problem1"]
+        pc["metrics_config"]["evaluate_frequency"] = 2
+        pc["optimizer_config"].update(outer_iterations=oits, **extra)
+        dist_mnist_ex.experiment(_write(meta, f"c{oits}{len(extra)}.yaml", conf))
+        out = sorted(glob.glob(os.path.join(meta, "*_dist_mnist_template")))[-1]
+        return torch.load(os.path.join(out, "dsgd_results.pt"), weights_only=False)
+
+    full = run("full", 6)
+    run("split", 4, checkpoint_every=2)
+    import time
+    time.sleep(1.0)
+    resumed = run("split", 6, resume=True)
+    assert resumed["forward_pass_count"][-1] == full["forward_pass_count"][-1]
+    assert torch.equal(resumed["validation_loss"][-1], full["validation_loss"][-1])
+    assert torch.equal(resumed["top1_accuracy"][-1], full["top1_accuracy"][-1])
+    # the first invocation evaluated at 0, 2 and its last round 3; the resumed one adds 4 and 5
+    assert len(resumed["validation_loss"]) == 5
 
 
 @pytest.fixture(scope="module")
