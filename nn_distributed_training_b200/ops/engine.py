@@ -197,6 +197,8 @@ class ConsensusEngine:
         # resident 64-round graphs 2.9 us / round, while the host-fed graphs (already forked per round for the
         # staging kernel) gain 1.9 us / round -> "auto" enables it only there.
         sp = opt.conf.get("separate_publish", pr.conf.get("separate_publish", "auto"))
+        if os.environ.get("NNDT_SEPARATE_PUBLISH") in ("0", "1"):       # A/B switch
+            sp = os.environ["NNDT_SEPARATE_PUBLISH"] == "1"
         if sp == "auto":
             sp = forked_graphs
         self.separate_publish = bool(ctx.world_size > 1 and sp)

@@ -12,6 +12,7 @@ block exchanged through the process group and opened by our runtime
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional
 
 import torch
@@ -37,6 +38,8 @@ class SymmetricBuffer:
         for s in self.shape:
             numel *= s
         try:
+            if os.environ.get("NNDT_SYMM", "symm_mem") == "ipc":      # A/B switch: plain cudaMalloc memory exported by CUDA IPC
+                raise RuntimeError("NNDT_SYMM=ipc")
             self._alloc_symm_mem(numel, dev)
         except Exception as e:  # noqa: BLE001
             self._symm_err = repr(e)

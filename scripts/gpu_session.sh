@@ -8,7 +8,7 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-add
 nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv -lms 500 > ${O}_smi.csv &
 SMI=$!
 if [[ " $* " == *" tests "* ]]; then
-  T=900 run python -m pytest tests -m gpu -x -q > ${O}_tests.log 2>&1
+  T=900 run python -m pytest tests -m gpu -q > ${O}_tests.log 2>&1
   tail -5 ${O}_tests.log
 fi
 if [[ " $* " == *" bench1 "* ]]; then
