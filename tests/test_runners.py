@@ -266,9 +266,42 @@ def test_visualization_summary_and_tools(tmp_path, monkeypatch):
     c = geo["centers"][(0, 0)]
     pts = ";".join(f"{c[0] + dx},{c[1] + dy}" for dx, dy in [(-30, -30), (30, -30), (30, 30), (-30, 30), (-30, -20)])
     out = os.path.join(str(tmp_path), "wp.npy")
-    ps.main(["x", p, out, "--points", pts])
+    ps.main(["x", p, out, "--points", pts, "--open"])
     wp = np.load(out)
     assert wp.shape == (5, 2) and np.abs(wp).max() <= 1.0
+
+
+def test_waypoint_path_editor_model(tmp_path):
+    """The editing operations of the polygon waypoint editor (reference floorplans/spline_paths/point_selector.py: drag,
+    'i' insert on an edge, 'd' delete, closed loop, numbered save) on the GUI-free model."""
+    from nn_distributed_training_b200.floorplans.spline_paths.point_selector import WaypointPath, point_segment_distance
+    assert abs(point_segment_distance((0, 1), (-1, 0), (1, 0)) - 1.0) < 1e-12
+    assert abs(point_segment_distance((3, 0), (-1, 0), (1, 0)) - 2.0) < 1e-12
+    # pixel space = 100 x data space, pick tolerance 5 px
+    path = WaypointPath(np.array([[0.0, 0.0], [1.0, 0.0], [1.0, 1.0], [0.0, 1.0]]), epsilon=5.0, to_pixels=lambda a: 100.0 * np.asarray(a))
+    assert path.xy.shape == (5, 2) and np.allclose(path.xy[0], path.xy[-1]) and path.n_vertices == 4
+    assert path.hit_test((1.02, 0.01)) == 1 and path.hit_test((0.5, 0.5)) is None
+    # dragging the first vertex drags the closing duplicate with it
+    path.move(0, (-0.1, -0.1))
+    assert np.allclose(path.xy[0], path.xy[-1]) and np.allclose(path.xy[0], [-0.1, -0.1])
+    # insert on the edge (1,0)-(1,1); a point away from every edge is refused
+    assert path.insert((0.5, 0.5)) is None
+    ind = path.insert((1.01, 0.5))
+    assert ind == 2 and path.n_vertices == 5 and np.allclose(path.xy[2], [1.01, 0.5])
+    # delete an interior vertex and the first vertex (the loop stays closed)
+    assert path.delete(2) and path.n_vertices == 4
+    assert path.delete(0) and path.n_vertices == 3 and np.allclose(path.xy[0], path.xy[-1])
+    assert not path.delete(1)                                  # a loop keeps at least three vertices
+    traj = path.spline(10)
+    assert traj.shape == (10 * (len(path.xy) - 1), 2) and np.isfinite(traj).all()
+    d = str(tmp_path / "tight_paths")
+    assert path.save(d).endswith("1.npy") and path.save(d).endswith("2.npy")
+    assert np.allclose(np.load(os.path.join(d, "2.npy")), path.xy)
+    # the shipped reference paths load into the editor model unchanged
+    ref = os.path.join(ROOT, "floorplans", "32_data", "tight_paths", "1.npy")
+    if os.path.exists(ref):
+        wp = np.load(ref)
+        assert WaypointPath(wp).xy.shape[0] in (len(wp), len(wp) + 1)
 
 
 def test_centralized_baseline(monkeypatch):
