@@ -29,7 +29,7 @@ static double getf(const py::dict& d, const char* k, double dflt = 0) { return d
 // ------------------------------------------------------------------ MNIST ----
 struct MnistOp {
   mnist::Args a{};
-  mnist::GenericShape gs{3, 5, 64, 0};
+  mnist::GenericShape gs{3, 5, 64, 0, 0.0, 1.0};
   int spb = 8, S = 1, eval_ctas = 1, generic = 0, tc = 0;
   alignas(64) unsigned char w1_map[128] = {0};
   explicit MnistOp(const py::dict& d) { update(d); }
@@ -49,7 +49,7 @@ struct MnistOp {
     // generic CUDA-core kernel (mnist_generic.cu): any conv shape, fp32 / fp64 (theta, grad_part, val_loss then address doubles)
     generic = geti(d, "generic", 0);
     gs.F = geti(d, "num_filters", 3); gs.KS = geti(d, "kernel_size", 5); gs.LW = geti(d, "linear_width", 64);
-    gs.dtype64 = geti(d, "dtype64", 0);
+    gs.dtype64 = geti(d, "dtype64", 0); gs.mean = getf(d, "mean"); gs.inv_std = getf(d, "inv_std", 1.0);
     // tcgen05 K-split cluster kernel (mnist_tc.cu): needs the W1 tensor map
     tc = geti(d, "tc", 0);
     if (tc) {
@@ -194,7 +194,7 @@ PYBIND11_MODULE(_C, m) {
               : consensus::launch_consensus_metric<float>(r, N, n_pad, local0, L, a, b, c, cur_stream()), "consensus_metric");
   });
   m.def("convnet_generic_smem_bytes", [](int F, int KS, int LW, int dtype64, int spb) {
-    return (size_t)mnist::generic_smem_bytes(mnist::GenericShape{F, KS, LW, dtype64}, dtype64, spb);
+    return (size_t)mnist::generic_smem_bytes(mnist::GenericShape{F, KS, LW, dtype64, 0.0, 1.0}, dtype64, spb);
   });
   m.def("make_w1_tensor_map", [](uint64_t theta, int n_pad, int L, int off_w1) {
     unsigned char buf[128];

@@ -54,7 +54,7 @@ struct GatherArgs {
 };
 // Generic CUDA-core conv net (mnist_generic.cu): any (num_filters <= 8, kernel_size in {3,5}, linear_width <= 128), fp32 or
 // fp64.  With dtype64 the Args pointers theta / grad_part / val_loss address doubles (loss_part stays float).
-struct GenericShape { int F, KS, LW, dtype64; };
+struct GenericShape { int F, KS, LW, dtype64; double mean, inv_std; };   // mean / inv_std in full precision for the fp64 arm
 size_t generic_smem_bytes(const GenericShape& gs, int dtype64, int spb);
 cudaError_t launch_generic_train(const Args& a, const GenericShape& gs, int spb, int S, cudaStream_t st);
 cudaError_t launch_generic_eval(const Args& a, const GenericShape& gs, int ctas_per_node, cudaStream_t st);

@@ -18,12 +18,13 @@ namespace {
 
 constexpr int GNT = 256;
 
-struct Dims { int F, KS, LW, CO, PO, NP, K1; };
+struct Dims { int F, KS, LW, CO, PO, NP, K1; double mean, inv_std; };
 
 __host__ __device__ inline Dims make_dims(const GenericShape& g) {
   Dims d;
   d.F = g.F; d.KS = g.KS; d.LW = g.LW;
   d.CO = HW - g.KS + 1; d.PO = d.CO / 2; d.NP = d.PO * d.PO; d.K1 = d.F * d.NP;
+  d.mean = g.mean; d.inv_std = g.inv_std;
   return d;
 }
 
@@ -86,7 +87,7 @@ NNDT_DEVINL void generic_chunk(Carve<T, SPB>& sm, const Args& a, const Dims& d, 
       const size_t base = (size_t)sm.sidx[s] * 784 + 4 * q;
       if (a.x_is_u8) {
         const uint32_t p = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const unsigned char*>(a.x) + base);
-        const T mean = (T)a.mean, is = (T)a.inv_std, sc = (T)1 / (T)255;
+        const T mean = (T)d.mean, is = (T)d.inv_std, sc = (T)1 / (T)255;
         v0 = ((T)(p & 0xff) * sc - mean) * is;
         v1 = ((T)((p >> 8) & 0xff) * sc - mean) * is;
         v2 = ((T)((p >> 16) & 0xff) * sc - mean) * is;

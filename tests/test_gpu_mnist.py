@@ -137,6 +137,7 @@ def test_fused_training_matches_torch_ops(cls, conf, graph):
 @pytest.mark.parametrize("conf", [DINNO, dict(DINNO, primal_optimizer="sgd", primal_iterations=3),
                                   dict(DINNO, primal_optimizer="adamw", persistant_primal_opt=True)])
 def test_dinno_round_cluster_kernel_matches_per_step_kernels(conf, graph, monkeypatch):
+    monkeypatch.setenv("NNDT_MNIST_TC", "0")        # the one-launch round kernel builds on the batch-split kernel
     """csrc/dinno_round.cu (opt-in: one cluster launch per round) vs the per-step kernels it replaces: same
     arithmetic, same partial-sum order -> the trained parameters agree to rounding."""
     monkeypatch.setenv("NNDT_SPB", "8")      # one cluster of 8 CTAs per node
@@ -358,6 +359,7 @@ def test_tc_kernel_matches_batch_split_kernel_and_autograd(B, float_inputs, monk
     """The tensor-core kernel (default for the paper shape at batch <= 64) against the mma.sync batch-split kernel
     (NNDT_MNIST_TC=0) and against PyTorch autograd: 3xTF32 keeps fp32-level agreement."""
     conf = {"alg_name": "dsgd", "alpha0": 0.01, "mu": 0.001, "outer_iterations": 2, "profile": False}
+    monkeypatch.setenv("NNDT_MNIST_TC", "1")
     tc = _problem(3, B, "fused", conf, M=150, float_inputs=float_inputs)
     monkeypatch.setenv("NNDT_MNIST_TC", "0")
     old = _problem(3, B, "fused", conf, M=150, float_inputs=float_inputs)
