@@ -60,7 +60,7 @@ struct MnistOp {
   }
   void train() {
     if (generic) check(mnist::launch_generic_train(a, gs, spb, S, cur_stream()), "convnet_generic_train");
-    else if (tc) check(mnist::launch_train_tc(a, w1_map, cur_stream()), "mnist_tc_train");
+    else if (tc) check(mnist::launch_train_tc(a, w1_map, S, cur_stream()), "mnist_tc_train");
     else check(mnist::launch_train(a, spb, S, cur_stream()), "mnist_train");
   }
   void eval() {

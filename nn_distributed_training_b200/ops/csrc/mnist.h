@@ -61,7 +61,7 @@ cudaError_t launch_generic_eval(const Args& a, const GenericShape& gs, int ctas_
 // tcgen05 / TMEM training kernel of the paper shape (mnist_tc.cu): K-split over a 6-CTA cluster per node, batch <= 64,
 // ONE gradient row per node (S = 1).  `w1_map128` = the 128-byte CUtensorMap written by make_w1_tensor_map.
 cudaError_t make_w1_tensor_map(const float* theta, int n_pad, int L, int off_w1, void* out_map128);
-cudaError_t launch_train_tc(const Args& a, const void* w1_map128, cudaStream_t st);
+cudaError_t launch_train_tc(const Args& a, const void* w1_map128, int nsplit, cudaStream_t st);
 int tc_max_active_clusters();
 cudaError_t launch_gather(const GatherArgs& a, cudaStream_t st);
 cudaError_t launch_train(const Args& a, int spb, int S, cudaStream_t st);

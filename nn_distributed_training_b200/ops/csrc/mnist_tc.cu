@@ -58,7 +58,7 @@ struct Smem {
   int label[64];
   float valid[64];
   unsigned char arg[64 * KC];
-  alignas(8) uint64_t bar_w, bar_m1, bar_m2;
+  alignas(8) uint64_t bar_w, bar_m1, bar_m2, bar_m3;
   uint32_t tmem_base;
 };
 static_assert(sizeof(Smem) + 1024 <= 227 * 1024, "shared memory budget");
@@ -111,9 +111,58 @@ NNDT_DEVINL void tma_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int
       : "memory");
 }
 
-// first / one-past-last sample whose fc2 part CTA r computes
-NNDT_DEVINL int own_lo(int r) { return (64 * r + 5) / 6; }
+// MN-major reading of 32-bit operands: the only layout the tensor core accepts is "128B swizzle with 32B atomicity"
+// (cute::UMMA::LayoutType::SWIZZLE_128B_BASE32B = 1: byte-address bits [5,7) ^= bits [7,9), atoms of 128 B x 4 rows), not
+// the 16B-chunk swizzle of the K-major layout.  The same tile is therefore re-swizzled IN PLACE between its K-major use
+// (forward) and its MN-major use (backward): a per-row permutation of the eight 16-byte chunks.
+NNDT_DEVINL uint64_t mn32desc(uint32_t op_base, int kk) {        // MN along the 128 B row (atoms SLAB apart), K = rows, 8 per MMA
+  uint64_t d = 0;
+  d |= (uint64_t)(((op_base + 1024u * (uint32_t)kk) & 0x3FFFF) >> 4);
+  d |= (uint64_t)((SLAB >> 4) & 0x3FFF) << 16;                   // leading byte offset: next 128 B-wide atom along MN
+  d |= (uint64_t)((512 >> 4) & 0x3FFF) << 32;                    // stride byte offset: next 4-row atom along K
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                                        // SWIZZLE_128B_BASE32B
+  return d;
+}
+// physical 16 B chunk of logical chunk c in row `row`: K-major (standard 128B swizzle) / MN-major (32B-base swizzle)
+NNDT_DEVINL int phys_k(int row, int c) { return c ^ (row & 7); }
+NNDT_DEVINL int phys_mn(int row, int c) { return ((((c >> 1) ^ (row & 3)) << 1) | (c & 1)); }
+// re-swizzle `nslab` slabs starting at `base` (hi and lo buffers are `lo_off` bytes apart) from the K-major to the
+// MN-major chunk order.  One 16 B chunk per thread and iteration; the eight chunks of a row sit in eight consecutive lanes.
+template <int NSLAB>
+NNDT_DEVINL void reswizzle_k_to_mn(unsigned char* base, uint32_t lo_off, int tid) {
+  constexpr int CH = 2 * NSLAB * 64 * 8, IT = (CH + NT - 1) / NT;
+  float4 v[IT];
+#pragma unroll
+  for (int i = 0; i < IT; ++i) {
+    const int o = tid + i * NT;
+    if (o < CH) {
+      const int buf = o / (NSLAB * 512), r = o - buf * (NSLAB * 512), slab = r >> 9, row = (r >> 3) & 63, p = r & 7;
+      v[i] = *reinterpret_cast<const float4*>(base + buf * lo_off + slab * SLAB + row * 128 + 16 * p);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < IT; ++i) {
+    const int o = tid + i * NT;
+    if (o < CH) {
+      const int buf = o / (NSLAB * 512), r = o - buf * (NSLAB * 512), slab = r >> 9, row = (r >> 3) & 63, p = r & 7;
+      const int c = p ^ (row & 7);                               // logical chunk held at physical position p
+      *reinterpret_cast<float4*>(base + buf * lo_off + slab * SLAB + row * 128 + 16 * phys_mn(row, c)) = v[i];
+    }
+  }
+}
 
+NNDT_DEVINL void stamp(long long* prof, int idx, int tid) {
+  if (prof != nullptr && tid == 0) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    prof[idx] = t;
+  }
+}
+
+// MS = samples per cluster (64 / batch splits per node): grid (CL, 64 / MS, L); the tensor-core tiles keep M = 64 rows
+template <int MS>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1)
 mnist_tc_train_kernel(const Args a, const __grid_constant__ CUtensorMap w1_map) {
   extern __shared__ unsigned char smem_raw[];
@@ -121,36 +170,41 @@ mnist_tc_train_kernel(const Args a, const __grid_constant__ CUtensorMap w1_map) 
   // cluster, so the peers' copies of every member sit at the same offset — what mapa needs)
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int l = blockIdx.y;
+  const int l = blockIdx.z, bsplit = blockIdx.y, nsplit = gridDim.y;
   const int c = (int)cluster_rank();                       // == blockIdx.x: K slice of this CTA
   const float* th = a.theta + (size_t)l * a.n_pad;
+  long long* prof = a.prof != nullptr ? a.prof + ((l * nsplit + bsplit) * CL + c) * 64 : nullptr;
+  stamp(prof, 0, tid);
+  auto own_lo = [](int r) { return (MS * r + CL - 1) / CL; };   // first sample whose fc2 part CTA r computes
 
   // ---- data half (before the programmatic-dependency wait: depends only on the dataset and the draw counter) ------
   const int call = a.calls != nullptr ? a.calls[l] : 0;
   const BatchGeom bg = batch_geom<true>(a, l, call);
-  if (tid < 64) {
+  if (tid < MS) {
     int idx = 0, lab = 0; float ok = 0.f;
-    if ((uint32_t)tid < bg.bs) {
+    const uint32_t t = (uint32_t)(bsplit * MS + tid);
+    if (t < bg.bs) {
       ok = 1.f;
-      idx = a.direct ? (int)(l * a.batch + tid) : bg.shard_off + (int)feistel_permute(bg.start + tid, bg.m, bg.key);
+      idx = a.direct ? (int)(l * a.batch + t) : bg.shard_off + (int)feistel_permute(bg.start + t, bg.m, bg.key);
       lab = (int)a.y[idx];
     }
     sm.sidx[tid] = idx; sm.valid[tid] = ok; sm.label[tid] = lab;
   }
   if (tid == 64) {
-    umma::mbar_init(&sm.bar_w, 1); umma::mbar_init(&sm.bar_m1, 1); umma::mbar_init(&sm.bar_m2, 1);
+    umma::mbar_init(&sm.bar_w, 1); umma::mbar_init(&sm.bar_m1, 1); umma::mbar_init(&sm.bar_m2, 1); umma::mbar_init(&sm.bar_m3, 1);
     umma::mbar_init_fence();
   }
   if (warp == 3) umma::tmem_alloc(&sm.tmem_base, TM_COLS);
   __syncthreads();
   // image rows 4c .. 4c+7 of every sample: 224 contiguous pixels
-  uint4 pu[2]; float4 pf[5];
+  constexpr int NU8 = (MS * 14 + NT - 1) / NT, NF4 = (MS * 56 + NT - 1) / NT;
+  uint4 pu[NU8]; float4 pf[NF4];
   if (a.x_is_u8) {
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NU8; ++i) {
       const int o = tid + i * NT;
       pu[i] = make_uint4(0, 0, 0, 0);
-      if (o < 64 * 14) {
+      if (o < MS * 14) {
         const int s = o / 14, q = o - s * 14;
         if (sm.valid[s] != 0.f)
           pu[i] = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(a.x) + (size_t)sm.sidx[s] * 784 + 112 * c + 16 * q);
@@ -158,19 +212,21 @@ mnist_tc_train_kernel(const Args a, const __grid_constant__ CUtensorMap w1_map) 
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
+    for (int i = 0; i < NF4; ++i) {
       const int o = tid + i * NT;
       pf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (o < 64 * 56) {
+      if (o < MS * 56) {
         const int s = o / 56, q = o - s * 56;
         if (sm.valid[s] != 0.f)
           pf[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.x) + (size_t)sm.sidx[s] * 784 + 112 * c + 4 * q);
       }
     }
   }
+  stamp(prof, 1, tid);
 
   pdl_wait();                 // the parameters of this step are final
   pdl_launch_dependents();
+  stamp(prof, 2, tid);
 
   // ---- W1 slice by TMA: three boxes [64 rows x 32 cols], one per channel, columns ch*144 + 24c .. +31 ---------------
   if (tid == 0) {
@@ -184,7 +240,7 @@ mnist_tc_train_kernel(const Args a, const __grid_constant__ CUtensorMap w1_map) 
   else if (tid < 78) sm.wc[tid] = __ldcg(th + a.off_bc + (tid - 75));
   else if (tid >= 96 && tid < 96 + HID) sm.b1[tid - 96] = __ldcg(th + a.off_b1 + (tid - 96));
   else if (tid >= 160 && tid < 160 + NCLS) sm.b2[tid - 160] = __ldcg(th + a.off_b2 + (tid - 160));
-  // zero columns 24..31 of every A atom (K padding)
+  // zero columns 24..31 of every A atom (K padding) for all 64 tile rows
   {
     const int buf = tid / 384, r = tid % 384, row = r / 6, k = r % 6, ch = k >> 1, chunk = 6 + (k & 1);
     unsigned char* base = (buf ? sm.a_lo : sm.a_hi) + ch * SLAB;
@@ -193,39 +249,40 @@ mnist_tc_train_kernel(const Args a, const __grid_constant__ CUtensorMap w1_map) 
   // pixels -> normalised fp32 in even/odd column planes
   if (a.x_is_u8) {
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NU8; ++i) {
       const int o = tid + i * NT;
-      if (o < 64 * 14) {
+      if (o < MS * 14) {
         const int s = o / 14, q = o - s * 14;
         const bool ok = sm.valid[s] != 0.f;
         const uint32_t w[4] = {pu[i].x, pu[i].y, pu[i].z, pu[i].w};
+        int row = (16 * q) / HW, col = 16 * q - row * HW;          // 16 consecutive pixels; a row has 28
+        float* xe = sm.xe + s * XP; float* xo = sm.xo + s * XP;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const int p = 16 * q + j, row = p / HW, col = p - row * HW;
           const float v = ok ? (((w[j >> 2] >> (8 * (j & 3))) & 0xff) * (1.f / 255.f) - a.mean) * a.inv_std : 0.f;
-          ((col & 1) ? sm.xo : sm.xe)[s * XP + row * 14 + (col >> 1)] = v;
+          ((col & 1) ? xo : xe)[row * 14 + (col >> 1)] = v;
+          if (++col == HW) { col = 0; ++row; }
         }
       }
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
+    for (int i = 0; i < NF4; ++i) {
       const int o = tid + i * NT;
-      if (o < 64 * 56) {
+      if (o < MS * 56) {
         const int s = o / 56, q = o - s * 56;
         const float v[4] = {pf[i].x, pf[i].y, pf[i].z, pf[i].w};
+        const int row = (4 * q) / HW, col = 4 * q - row * HW;      // 28 = 7 x 4: a float4 never straddles a row
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int p = 4 * q + j, row = p / HW, col = p - row * HW;
-          ((col & 1) ? sm.xo : sm.xe)[s * XP + row * 14 + (col >> 1)] = v[j];
-        }
+        for (int j = 0; j < 4; ++j) (((col + j) & 1) ? sm.xo : sm.xe)[s * XP + row * 14 + ((col + j) >> 1)] = v[j];
       }
     }
   }
   __syncthreads();
+  stamp(prof, 3, tid);
 
   // ---- conv + ReLU + maxpool: one (sample, pooled cell) per item, all three channels from one 6x6 patch ------------
-  for (int it = tid; it < 64 * CELLS; it += NT) {
+  for (int it = tid; it < MS * CELLS; it += NT) {
     const int s = it / CELLS, cell = it - s * CELLS;
     const int pr = cell / PHW, px = cell - pr * PHW;
     float patch[6][6];
@@ -264,6 +321,7 @@ mnist_tc_train_kernel(const Args a, const __grid_constant__ CUtensorMap w1_map) 
       sm.arg[s * KC + ch * CELLS + cell] = (unsigned char)(ai | (m > 0.f ? 4 : 0));
     }
   }
+  stamp(prof, 4, tid);
   // ---- W1 slice: raw fp32 -> hi (in place) + lo -----------------------------------------------------------------------
   mbarrier_wait_parity(&sm.bar_w, 0);
 #pragma unroll
@@ -296,11 +354,12 @@ mnist_tc_train_kernel(const Args a, const __grid_constant__ CUtensorMap w1_map) 
   }
   umma::mbar_wait(&sm.bar_m1, 0);
   umma::fence_after_sync();
+  stamp(prof, 5, tid);
   if (warp < 8) {                                        // TMEM lane of row s: 32 (s / 16) + s % 16
     const int q = warp & 3, half = warp >> 2;
     float v[32];
     umma::tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + TM_D1 + 32 * half, v);
-    if (lane < 16) {
+    if (lane < 16 && 16 * q + lane < MS) {
       float* dst = sm.hpart + (16 * q + lane) * HP_STRIDE + 32 * half;
 #pragma unroll
       for (int i = 0; i < 32; ++i) dst[i] = v[i];
@@ -309,7 +368,12 @@ mnist_tc_train_kernel(const Args a, const __grid_constant__ CUtensorMap w1_map) 
   umma::fence_before_sync();
   cluster_sync();                                        // #1: all six partial H are in shared memory
   umma::fence_after_sync();
-  if (c == 0 && tid == 0 && a.calls != nullptr) a.calls[l] = call + 1;    // every CTA of the node has read the counter
+  stamp(prof, 6, tid);
+  if (c == 0 && tid == 0 && a.calls != nullptr) {
+    // every CTA of this cluster has read the draw counter; the last cluster of the node to get here advances it
+    if (a.arrive == nullptr || nsplit == 1) a.calls[l] = call + 1;
+    else if (atomicAdd(a.arrive + l, 1u) == (unsigned)nsplit - 1) { a.arrive[l] = 0; a.calls[l] = call + 1; }
+  }
 
   // ---- reduce-scatter of H over the cluster + fc2 / loss / their backward for this CTA's samples -----------------------
   const int s0 = own_lo(c), ns = own_lo(c + 1) - s0;
@@ -361,19 +425,6 @@ mnist_tc_train_kernel(const Args a, const __grid_constant__ CUtensorMap w1_map) 
     sm.dh_loc[tid] = sm.h_loc[tid] > 0.f ? v : 0.f;
   }
   __syncthreads();
-  // push the dH rows (hi / lo) into the operand buffers of ALL six CTAs: 16-byte chunk (row s, 4 columns) per thread
-  if (tid < ns * 16) {
-    const int sl = tid >> 4, ch4 = tid & 15, s = s0 + sl;
-    const float4 v = *reinterpret_cast<const float4*>(sm.dh_loc + sl * HID + 4 * ch4);
-    float4 h4, l4;
-    split(v.x, h4.x, l4.x); split(v.y, h4.y, l4.y); split(v.z, h4.z, l4.z); split(v.w, h4.w, l4.w);
-    const uint32_t off = (uint32_t)(ch4 >> 3) * SLAB + umma::swz_chunk_off(s, ch4 & 7);
-#pragma unroll
-    for (int r = 0; r < CL; ++r) {
-      st_dsmem4(map_to(sm.dh_hi + off, (uint32_t)r), h4);
-      st_dsmem4(map_to(sm.dh_lo + off, (uint32_t)r), l4);
-    }
-  }
   // this CTA's share of the fc2 / b1 gradients and of the loss
   for (int o = tid; o < NCLS * HID; o += NT) {
     const int cc = o >> 6, j = o & 63;
@@ -394,45 +445,81 @@ mnist_tc_train_kernel(const Args a, const __grid_constant__ CUtensorMap w1_map) 
     for (int sl = 0; sl < ns; ++sl) v += sm.red[sl];
     sm.part[PART_LOSS] = v * bg.inv_bs;
   }
-  fence_proxy_async_all();                               // the pushed dH rows feed the tensor cores of the peers
-  cluster_sync();                                        // #2: every CTA holds all 64 dH rows; hpart is free again
-  fence_proxy_async_all();
+  stamp(prof, 7, tid);
+  cluster_sync();                                        // #2: every owner's dH rows are final; hpart is free again
+  stamp(prof, 8, tid);
 
-  // ---- MMA 2: da1_c[64 s x 96] = dH . W1_c (A K-major, B MN-major);  MMA 3: dW1_c[64 j x 96] = dH^T . A_c (both MN-major) --
+  // ---- gather all MS dH rows from their owners (DSMEM reads) into the local K-major operand tile (hi / lo), and
+  //      re-swizzle the W1 slice for its MN-major use (W is dead as a K-major operand: MMA 1 has completed) -------------
+  for (int o = tid; o < MS * 16; o += NT) {
+    const int s = o >> 4, ch4 = o & 15;
+    int r = 0;
+#pragma unroll
+    for (int q = 1; q < CL; ++q) r += (s >= own_lo(q)) ? 1 : 0;
+    const uint32_t src = map_to(sm.dh_loc + (s - own_lo(r)) * HID + 4 * ch4, (uint32_t)r);
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(src) : "memory");
+    float4 h4, l4;
+    split(v.x, h4.x, l4.x); split(v.y, h4.y, l4.y); split(v.z, h4.z, l4.z); split(v.w, h4.w, l4.w);
+    const uint32_t off = (uint32_t)(ch4 >> 3) * SLAB + umma::swz_chunk_off(s, ch4 & 7);
+    *reinterpret_cast<float4*>(sm.dh_hi + off) = h4;
+    *reinterpret_cast<float4*>(sm.dh_lo + off) = l4;
+  }
+  reswizzle_k_to_mn<3>(sm.w_hi, (uint32_t)(sm.w_lo - sm.w_hi), tid);
+  umma::fence_async_smem();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  stamp(prof, 9, tid);
+
+  // ---- MMA 2: da1_c[64 s x 96] = dH . W1_c (A K-major, B MN-major) ------------------------------------------------------
   if (tid == 0) {
-    umma::fence_after_sync();
-    constexpr uint32_t id2 = idesc_tf32(64, 96, false, true), id3 = idesc_tf32(64, 96, true, true);
+    constexpr uint32_t id2 = idesc_tf32(64, 96, false, true);
     bool acc = false;
 #pragma unroll
     for (int pass = 0; pass < 3; ++pass) {
       const uint32_t D = pass == 0 ? DH_LO : DH_HI, W = pass == 1 ? W_LO : W_HI;
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk) { mma_tf32(tmem + TM_D2, kdesc(D, kk), mndesc(W, kk), id2, acc); acc = true; }
+      for (int kk = 0; kk < 8; ++kk) { mma_tf32(tmem + TM_D2, kdesc(D, kk), mn32desc(W, kk), id2, acc); acc = true; }
     }
-    acc = false;
+    umma::commit(&sm.bar_m2);
+  }
+  // under MMA 2: the A tile (dead as a K-major operand) moves to the MN-major chunk order for MMA 3
+  reswizzle_k_to_mn<3>(sm.a_hi, (uint32_t)(sm.a_lo - sm.a_hi), tid);
+  umma::mbar_wait(&sm.bar_m2, 0);
+  umma::fence_after_sync();
+  // MMA 2 is done with the K-major dH: same tile, MN-major order, for dW1 = dH^T . A
+  reswizzle_k_to_mn<2>(sm.dh_hi, (uint32_t)(sm.dh_lo - sm.dh_hi), tid);
+  umma::fence_async_smem();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  stamp(prof, 10, tid);
+
+  // ---- MMA 3: dW1_c[64 j x 96] = dH^T . A_c (both MN-major; K = the MS sample rows) ---------------------------------------
+  if (tid == 0) {
+    constexpr uint32_t id3 = idesc_tf32(64, 96, true, true);
+    bool acc = false;
 #pragma unroll
     for (int pass = 0; pass < 3; ++pass) {
       const uint32_t D = pass == 0 ? DH_LO : DH_HI, A = pass == 1 ? A_LO : A_HI;
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk) { mma_tf32(tmem + TM_D3, mndesc(D, kk), mndesc(A, kk), id3, acc); acc = true; }
+      for (int kk = 0; kk < MS / 8; ++kk) { mma_tf32(tmem + TM_D3, mn32desc(D, kk), mn32desc(A, kk), id3, acc); acc = true; }
     }
-    umma::commit(&sm.bar_m2);
+    umma::commit(&sm.bar_m3);
   }
-  umma::mbar_wait(&sm.bar_m2, 0);
-  umma::fence_after_sync();
-  float* gp = a.grad_part + (size_t)l * a.n_pad;
+  float* gp = a.grad_part + ((size_t)l * nsplit + bsplit) * a.n_pad;
+  // 24 warps: TMEM quarter q, 16 accumulator columns each: channel atom ch, half of its 32 columns
+  const int eq = warp & 3, esub = warp >> 2, ech = esub >> 1, ehalf = esub & 1;
+  const int erow = 16 * eq + lane;                       // valid for lane < 16
+  const int nvalid = ehalf ? 8 : 16;                     // cells 16..23 of the second half, 24..31 are padding
   {
-    // 24 warps: TMEM quarter q, 16 accumulator columns each: channel atom ch, half of its 32 columns
-    const int q = warp & 3, sub = warp >> 2, ch = sub >> 1, half = sub & 1;
-    const int row = 16 * q + lane;                       // valid for lane < 16
-    float v2[16], v3[16];
-    umma::tmem_ld16(tmem + ((uint32_t)(32 * q) << 16) + TM_D2 + 32 * ch + 16 * half, v2);
-    umma::tmem_ld16(tmem + ((uint32_t)(32 * q) << 16) + TM_D3 + 32 * ch + 16 * half, v3);
-    if (lane < 16) {
-      const int nvalid = half ? 8 : 16;                  // cells 16..23 of the second half, 24..31 are padding
-      float* d1 = sm.hpart + row * KC + ch * CELLS + 16 * half;
-      const unsigned char* ag = sm.arg + row * KC + ch * CELLS + 16 * half;
-      float* gw = gp + a.off_w1 + row * FC1_IN + ch * NPOOL + CELLS * c + 16 * half;
+    // under MMA 3: da1 (D2) -> shared memory, masked by ReLU'(a1)
+    float v2[16];
+    umma::tmem_ld16(tmem + ((uint32_t)(32 * eq) << 16) + TM_D2 + 32 * ech + 16 * ehalf, v2);
+    if (lane < 16 && erow < MS) {
+      float* d1 = sm.hpart + erow * KC + ech * CELLS + 16 * ehalf;
+      const unsigned char* ag = sm.arg + erow * KC + ech * CELLS + 16 * ehalf;
 #pragma unroll
       for (int i = 0; i < 16; i += 4) {
         if (i < nvalid) {
@@ -440,20 +527,33 @@ mnist_tc_train_kernel(const Args a, const __grid_constant__ CUtensorMap w1_map) 
           d.x = (ag[i] & 4) ? v2[i] : 0.f; d.y = (ag[i + 1] & 4) ? v2[i + 1] : 0.f;
           d.z = (ag[i + 2] & 4) ? v2[i + 2] : 0.f; d.w = (ag[i + 3] & 4) ? v2[i + 3] : 0.f;
           *reinterpret_cast<float4*>(d1 + i) = d;
-          *reinterpret_cast<float4*>(gw + i) = make_float4(v3[i], v3[i + 1], v3[i + 2], v3[i + 3]);
         }
       }
     }
   }
+  umma::mbar_wait(&sm.bar_m3, 0);
+  umma::fence_after_sync();
+  stamp(prof, 11, tid);
+  {
+    float v3[16];
+    umma::tmem_ld16(tmem + ((uint32_t)(32 * eq) << 16) + TM_D3 + 32 * ech + 16 * ehalf, v3);
+    if (lane < 16) {
+      float* gw = gp + a.off_w1 + erow * FC1_IN + ech * NPOOL + CELLS * c + 16 * ehalf;
+#pragma unroll
+      for (int i = 0; i < 16; i += 4)
+        if (i < nvalid) *reinterpret_cast<float4*>(gw + i) = make_float4(v3[i], v3[i + 1], v3[i + 2], v3[i + 3]);
+    }
+  }
   umma::fence_before_sync();
   __syncthreads();        // da1 complete; the operand slabs are dead: they become the scratch of the conv-grad reduce
+  stamp(prof, 12, tid);
   // ---- conv grads: each pooled cell routes da1 to its argmax conv position (3 groups of 256 threads, one per channel) ----
   float cacc[26];
 #pragma unroll
   for (int i = 0; i < 26; ++i) cacc[i] = 0.f;
   const int cg = tid / CGROUP, ct = tid - cg * CGROUP;
   if (cg < F) {
-    for (int it = ct; it < 64 * CELLS; it += CGROUP) {
+    for (int it = ct; it < MS * CELLS; it += CGROUP) {
       const int s = it / CELLS, cell = it - s * CELLS;
       const float g = sm.hpart[s * KC + cg * CELLS + cell];
       if (g != 0.f) {
@@ -487,6 +587,7 @@ mnist_tc_train_kernel(const Args a, const __grid_constant__ CUtensorMap w1_map) 
       sm.part[(i < 25) ? PART_WC + ch * 25 + i : PART_BC + ch] = v;
     }
   }
+  stamp(prof, 13, tid);
   cluster_sync();                                        // #3: every CTA's share of the small gradients is in `part`
   if (c == 0) {
     for (int o = tid; o < PART_N; o += NT) {
@@ -499,13 +600,14 @@ mnist_tc_train_kernel(const Args a, const __grid_constant__ CUtensorMap w1_map) 
       else if (o < PART_B2) gp[a.off_w2 + (o - PART_W2)] = v;
       else if (o < PART_LOSS) gp[a.off_b2 + (o - PART_B2)] = v;
       else {
-        a.loss_part[l] = v;
-        if (a.loss_mirror != nullptr) a.loss_mirror[l] = v;     // zero-copy store to pinned host memory
+        a.loss_part[l * nsplit + bsplit] = v;
+        if (a.loss_mirror != nullptr) a.loss_mirror[l * nsplit + bsplit] = v;     // zero-copy store to pinned host memory
       }
     }
   }
   cluster_sync();                                        // #4: rank 0 is done reading the peers' shared memory
   if (warp == 3) umma::tmem_dealloc(tmem, TM_COLS);
+  stamp(prof, 14, tid);
 }
 
 }  // namespace tc
@@ -536,12 +638,13 @@ cudaError_t make_w1_tensor_map(const float* theta, int n_pad, int L, int off_w1,
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-cudaError_t launch_train_tc(const Args& a, const void* w1_map128, cudaStream_t st) {
-  static cudaError_t prep = cudaFuncSetAttribute(tc::mnist_tc_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+template <int MS>
+static cudaError_t launch_tc_ms(const Args& a, const void* w1_map128, cudaStream_t st) {
+  static cudaError_t prep = cudaFuncSetAttribute(tc::mnist_tc_train_kernel<MS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)sizeof(tc::Smem) + 1024);
   if (prep != cudaSuccess) return prep;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(tc::CL, a.L); cfg.blockDim = dim3(tc::NT);
+  cfg.gridDim = dim3(tc::CL, 64 / MS, a.L); cfg.blockDim = dim3(tc::NT);
   cfg.dynamicSmemBytes = sizeof(tc::Smem) + 1024; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -550,18 +653,28 @@ cudaError_t launch_train_tc(const Args& a, const void* w1_map128, cudaStream_t s
   cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
   CUtensorMap map;
   memcpy(&map, w1_map128, sizeof(map));
-  return cudaLaunchKernelEx(&cfg, tc::mnist_tc_train_kernel, a, map);
+  return cudaLaunchKernelEx(&cfg, tc::mnist_tc_train_kernel<MS>, a, map);
+}
+
+// `nsplit` batch splits per node (1, 2 or 4): 6 * nsplit CTAs per node, `nsplit` gradient partial rows
+cudaError_t launch_train_tc(const Args& a, const void* w1_map128, int nsplit, cudaStream_t st) {
+  switch (nsplit) {
+    case 1: return launch_tc_ms<64>(a, w1_map128, st);
+    case 2: return launch_tc_ms<32>(a, w1_map128, st);
+    case 4: return launch_tc_ms<16>(a, w1_map128, st);
+  }
+  return cudaErrorInvalidValue;
 }
 
 int tc_max_active_clusters() {
-  if (cudaFuncSetAttribute(tc::mnist_tc_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tc::Smem) + 1024) != cudaSuccess) {
+  if (cudaFuncSetAttribute(tc::mnist_tc_train_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tc::Smem) + 1024) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(tc::CL, 1); cfg.blockDim = dim3(tc::NT); cfg.dynamicSmemBytes = sizeof(tc::Smem) + 1024;
+  cfg.gridDim = dim3(tc::CL, 1, 1); cfg.blockDim = dim3(tc::NT); cfg.dynamicSmemBytes = sizeof(tc::Smem) + 1024;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, tc::mnist_tc_train_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (cudaOccupancyMaxActiveClusters(&n, tc::mnist_tc_train_kernel<64>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
   return n;
 }
 

@@ -56,8 +56,11 @@ class FusedMnist:
         self.tc = (not self.generic and self.B <= 64 and os.environ.get("NNDT_MNIST_TC", "0") != "0"
                    and str(problem.conf.get("mnist_kernel", "tc")) == "tc" and self.ext.mnist_tc_max_clusters() >= 1)
         if self.tc:
-            self.S = 1
-        self.kernel_name = ("mnist_tc_train_kernel (tcgen05 kind::tf32 3xTF32, TMEM, TMA tensor map, 6-CTA cluster per node)" if self.tc
+            # batch splits per node (1, 2 or 4 clusters of 6 CTAs, M = 64 / 32 / 16 samples each): as many as keep all
+            # 6 * nsplit * L CTAs in one wave — the conv / conv-grad phases are CUDA-core work that scales with SMs
+            want = int(os.environ.get("NNDT_TC_SPLIT", "0"))
+            self.S = want if want in (1, 2, 4) else max([n for n in (1, 2, 4) if 6 * n * self.L <= sms] or [1])
+        self.kernel_name = (f"mnist_tc_train_kernel<{64 // self.S}> (tcgen05 kind::tf32 3xTF32, TMEM, TMA tensor map, {self.S} x 6-CTA cluster per node)" if self.tc
                             else "convnet_generic_kernel (CUDA cores)" if self.generic else "mnist_kernel (mma.sync 3xTF32)")
         sh = problem.shards
         self.x = sh.x.reshape(sh.x.shape[0], -1).contiguous()
@@ -92,7 +95,7 @@ class FusedMnist:
         if self.tc:
             self.base.update(tc=1, w1_map=self.ext.make_w1_tensor_map(a.theta.data_ptr(), a.n_pad, self.L, off[names[2]]))
         if os.environ.get("NNDT_STEP_PROF") == "1":     # scripts/profile_round_phases.py --per-step
-            self.step_prof = torch.zeros(self.L * self.S, 64, dtype=torch.int64, device=dev)
+            self.step_prof = torch.zeros(self.L * self.S * (6 if self.tc else 1), 64, dtype=torch.int64, device=dev)
             self.base["step_prof"] = self.step_prof.data_ptr()
         self.train_op = self.ext.MnistOp(self.base)
         self._setup_eval()
@@ -222,7 +225,7 @@ class FusedMnist:
         # a training CTA fills an SM's register file (768 threads x 80 registers): a staging block that lands on
         # an SM evicts a training CTA into a second wave, so the staging grid is sized to the SMs left over
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        ctas = self.L * (6 if self.tc else self.S)
+        ctas = self.L * self.S * (6 if self.tc else 1)
         free = sms - ctas if ctas <= sms else 0      # multi-wave grids leave no SM idle
         gather_blocks = int(os.environ.get("NNDT_GATHER_BLOCKS", "0")) or max(8, min(24, free - 2))
         self.direct_ops, self.gather_ops = [], []
