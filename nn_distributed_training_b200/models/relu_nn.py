@@ -34,10 +34,25 @@ class _FFNet(nn.Module):
         factory = {"relu": lambda: nn.ReLU(inplace=True), "tanh": nn.Tanh, "sigmoid": nn.Sigmoid}[a]
         self.seq = _stack(self.shape, factory, self._act_on_last, dtype)
 
+    def _layer_acts(self):
+        n = len(self.shape) - 1
+        return [self._act if (li != n - 1 or self._act_on_last) else "none" for li in range(n)]
+
     def forward(self, x):
         if self.coerce_numpy and isinstance(x, np.ndarray):
             p = next(self.parameters())
             x = torch.as_tensor(x, dtype=p.dtype, device=p.device)
+        if x.is_cuda:
+            # CUDA: the whole network is one fused forward launch and one fused backward launch
+            # (ops/csrc/mlp_generic.cu); NNDT_FUSED_MLP=0 or an unsupported width falls back to nn.Sequential loudly
+            from ..ops import mlp_generic as mg
+            acts = self._layer_acts()
+            if mg.enabled() and mg.supported(self.shape, acts, x.dtype):
+                return mg.fused_mlp(x, [p for p in self.seq.parameters()], self.shape, acts)
+            if not getattr(self, "_warned", False):
+                self._warned = True
+                print(f"[nndt] WARNING: {type(self).__name__}{self.shape} ({x.dtype}) runs nn.Sequential (cuBLAS) on CUDA: "
+                      "no fused kernel for this shape / dtype or NNDT_FUSED_MLP=0", flush=True)
         return self.seq(x)
 
 

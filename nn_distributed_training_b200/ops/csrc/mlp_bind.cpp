@@ -6,6 +6,7 @@
 
 #include "mlp.h"
 #include "lidar.h"
+#include "mlp_generic.h"
 
 namespace py = pybind11;
 using namespace nndt;
@@ -57,7 +58,35 @@ static lidar::Args lidar_args(const py::dict& d) {
   return a;
 }
 
+static mlpg::Args generic_args(const py::dict& d) {
+  mlpg::Args a{};
+  a.x = ptr<const void>(d, "x"); a.params = ptr<const void>(d, "params");
+  a.M = geti(d, "M"); a.dtype64 = geti(d, "dtype64");
+  auto dims = d["dims"].cast<std::vector<int>>();
+  auto act = d["act"].cast<std::vector<int>>();
+  auto w_off = d["w_off"].cast<std::vector<int>>();
+  auto b_off = d["b_off"].cast<std::vector<int>>();
+  a.nl = (int)dims.size() - 1;
+  if (a.nl < 1 || a.nl > mlpg::kMaxLayers || (int)act.size() != a.nl || (int)w_off.size() != a.nl || (int)b_off.size() != a.nl)
+    throw std::runtime_error("mlp_generic: bad layer description");
+  int off = 0;
+  for (int l = 0; l <= a.nl; ++l) a.dims[l] = dims[l];
+  for (int l = 0; l < a.nl; ++l) {
+    a.act[l] = act[l]; a.w_off[l] = w_off[l]; a.b_off[l] = b_off[l];
+    a.act_off[l] = off; off += dims[l + 1];
+  }
+  a.act_stride = off;
+  a.acts = ptr<void>(d, "acts"); a.gout = ptr<const void>(d, "gout"); a.gparams = ptr<void>(d, "gparams"); a.gx = ptr<void>(d, "gx");
+  return a;
+}
+
 void bind_mlp(py::module& m) {
+  m.def("mlp_generic_forward", [](const py::dict& d) {
+    check(mlpg::launch_forward(generic_args(d), at::cuda::getCurrentCUDAStream().stream()), "mlp_generic_forward");
+  });
+  m.def("mlp_generic_backward", [](const py::dict& d) {
+    check(mlpg::launch_backward(generic_args(d), at::cuda::getCurrentCUDAStream().stream()), "mlp_generic_backward");
+  });
   m.def("lidar_scan", [](const py::dict& d) {
     check(lidar::launch_scan(lidar_args(d), at::cuda::getCurrentCUDAStream().stream()), "lidar_scan");
   });

@@ -156,3 +156,55 @@ def test_gpu_lidar_matches_cpu_scans(tmp_path):
     gpu = lidar.scan_batch(traj, device=DEV)
     assert gpu.shape == cpu.shape
     np.testing.assert_allclose(gpu, cpu, rtol=0, atol=1e-7)
+
+
+# ---- generic CUDA-core MLP kernels (csrc/mlp_generic.cu): any widths <= 256, ReLU / Tanh / Sigmoid, fp32 / fp64 ---------
+@pytest.mark.parametrize("cls_name,shape,dtype,M", [
+    ("FFReLUNet", [12, 64, 64, 64, 5], torch.float32, 2400),        # RL actor (reference RL/dist_rl/model.py)
+    ("FFReLUNet", [12, 64, 64, 64, 1], torch.float32, 777),         # RL critic, ragged last tile
+    ("FFTanhNet", [2, 37, 129, 3], torch.float64, 100),
+    ("FFSigmoidNet", [7, 256, 16, 8], torch.float32, 65),
+    ("FFReLUNet", [2, 200, 1], torch.float64, 33),
+])
+def test_generic_mlp_kernels_match_autograd(cls_name, shape, dtype, M, monkeypatch):
+    from nn_distributed_training_b200.models import relu_nn
+    torch.manual_seed(0)
+    net = getattr(relu_nn, cls_name)(shape, dtype=dtype).to(DEV)
+    x = torch.randn(M, shape[0], dtype=dtype, device=DEV, requires_grad=True)
+    w = torch.randn(M, shape[-1], dtype=dtype, device=DEV)
+    out = net(x)                                   # fused: ops/mlp_generic.py
+    (out * w).sum().backward()
+    g_fused = [p.grad.clone() for p in net.parameters()]
+    gx_fused = x.grad.clone()
+    for p in net.parameters():
+        p.grad = None
+    x.grad = None
+    monkeypatch.setenv("NNDT_FUSED_MLP", "0")
+    ref = net(x)                                   # nn.Sequential
+    (ref * w).sum().backward()
+    tol = dict(rtol=1e-9, atol=1e-10) if dtype == torch.float64 else dict(rtol=2e-3, atol=2e-4)
+    torch.testing.assert_close(out, ref, **tol)
+    torch.testing.assert_close(gx_fused, x.grad, **tol)
+    for a, p in zip(g_fused, net.parameters()):
+        scale = p.grad.abs().max().clamp_min(1e-6)
+        assert ((a - p.grad).abs().max() / scale).item() < (1e-8 if dtype == torch.float64 else 2e-3)
+
+
+def test_rl_problem_runs_fused_mlp_kernels_on_cuda():
+    """The distributed-PPO trainers on CUDA: actor / critic forward + backward go through the fused MLP kernels
+    (one DiNNO round of the RL problem, finite parameters afterwards)."""
+    import networkx as nx
+    from nn_distributed_training_b200.rl.consensus_ppo import DiNNOPPO
+    from nn_distributed_training_b200.rl.dist_ppo import DistPPOProblem
+    from nn_distributed_training_b200.rl.model import FFReLUNet
+    from nn_distributed_training_b200.rl.simple_tag import SimpleTagEnv
+    env = SimpleTagEnv(num_envs=8, num_good=1, num_adversaries=3, num_obstacles=8, max_cycles=40, device=DEV, seed=0)
+    pr = DistPPOProblem(FFReLUNet([12, 64, 64, 64, 5]), FFReLUNet([12, 64, 64, 64, 1]), nx.wheel_graph(3), env,
+                        timesteps_per_batch=400, max_timesteps_per_episode=40, gamma=0.99, n_updates_per_iteration=2, lr=3e-4,
+                        clip=0.2, seed=0)
+    conf = dict(max_rl_timesteps=800, ID=0, out_dir="/tmp/nndt_rl_test", writeout=False, rho_init=1.0, rho_scaling=1.0,
+                primal_lr_start=3e-4, primal_lr_finish=1e-3, lr_decay_type="constant", persistant_primal_opt=False,
+                primal_iterations=2, outer_iterations=10 ** 6)
+    DiNNOPPO(pr, torch.device(DEV), conf).train()
+    for m in pr.models.values():
+        assert all(torch.isfinite(p).all() for p in m.parameters())
