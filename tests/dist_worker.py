@@ -58,7 +58,9 @@ def delayed(ctx, N, G, backend):
             data = synthetic_mnist(200 * N, seed=3)
             val = synthetic_mnist(128, seed=4)
             shards = [data.select(torch.arange(i * 200, (i + 1) * 200)) for i in range(N)]
-            pconf = {"problem_name": "t", "train_batch_size": 32, "val_batch_size": 64, "metrics": METRICS,
+            # same samples-per-CTA split in the distributed and the single-process run: identical fp32 partial sums, so the
+            # comparison is exact and not blurred by Adam amplifying summation-order round-off
+            pconf = {"problem_name": "t", "train_batch_size": 32, "val_batch_size": 64, "metrics": METRICS, "samples_per_cta": 8,
                      "metrics_config": {"evaluate_frequency": 10 ** 6}, "optimizer_config": conf, **extra}
             torch.manual_seed(5)
             return DistMNISTProblem(G, MNISTConvNet(3, 5, 64), torch.nn.NLLLoss(), shards, val, c.device, pconf, ctx=c,
