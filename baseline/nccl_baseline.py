@@ -173,6 +173,4 @@ def run(args, metric, nodes_per_gpu, batch, pits, opt_conf, shard_fn):
     import sys
     sys.stdout.flush()
     sys.stderr.flush()
-    if dist.is_initialized():
-        dist.barrier()
     os._exit(0)
