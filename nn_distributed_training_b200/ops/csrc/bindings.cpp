@@ -30,7 +30,7 @@ static double getf(const py::dict& d, const char* k, double dflt = 0) { return d
 struct MnistOp {
   mnist::Args a{};
   mnist::GenericShape gs{3, 5, 64, 0, 0.0, 1.0};
-  int spb = 8, S = 1, eval_ctas = 1, generic = 0, tc = 0;
+  int spb = 8, S = 1, eval_ctas = 1, generic = 0, tc = 0, cl64 = 0;
   alignas(64) unsigned char w1_map[128] = {0};
   explicit MnistOp(const py::dict& d) { update(d); }
   void update(const py::dict& d) {
@@ -51,6 +51,7 @@ struct MnistOp {
     gs.F = geti(d, "num_filters", 3); gs.KS = geti(d, "kernel_size", 5); gs.LW = geti(d, "linear_width", 64);
     gs.dtype64 = geti(d, "dtype64", 0); gs.mean = getf(d, "mean"); gs.inv_std = getf(d, "inv_std", 1.0);
     // tcgen05 K-split cluster kernel (mnist_tc.cu): needs the W1 tensor map
+    cl64 = geti(d, "cl64", 0);
     tc = geti(d, "tc", 0);
     if (tc) {
       const std::string m = d["w1_map"].cast<py::bytes>();
@@ -59,7 +60,8 @@ struct MnistOp {
     }
   }
   void train() {
-    if (generic) check(mnist::launch_generic_train(a, gs, spb, S, cur_stream()), "convnet_generic_train");
+    if (cl64) check(mnist::launch_train_cl64(a, gs, S, cur_stream()), "mnist_cl64_train");
+    else if (generic) check(mnist::launch_generic_train(a, gs, spb, S, cur_stream()), "convnet_generic_train");
     else if (tc) check(mnist::launch_train_tc(a, w1_map, S, cur_stream()), "mnist_tc_train");
     else check(mnist::launch_train(a, spb, S, cur_stream()), "mnist_train");
   }
@@ -202,6 +204,7 @@ PYBIND11_MODULE(_C, m) {
     return py::bytes(reinterpret_cast<const char*>(buf), 128);
   });
   m.def("mnist_tc_max_clusters", []() { return mnist::tc_max_active_clusters(); });
+  m.def("mnist_cl64_max_clusters", []() { return mnist::cl64_max_active_clusters(); });
   m.def("rank_barrier", [](uint64_t slots, uint64_t peer_slot, int world, int rank, int epoch, uint64_t gate, uint64_t err) {
     check(consensus::launch_rank_barrier(reinterpret_cast<int*>(slots), reinterpret_cast<const int64_t*>(peer_slot), world, rank,
                                          epoch, reinterpret_cast<const volatile int*>(gate), reinterpret_cast<int*>(err), cur_stream()),

@@ -1,0 +1,461 @@
+// float64 training kernel of the paper's MNISTConvNet(3, 5, 64) at batch <= 64: the K-split thread-block-cluster
+// decomposition of mnist_tc.cu with the contractions on the fp64 CUDA cores (B200 has no fp64 tcgen05 path; its fp64
+// tensor and vector rates are the same 64 DFMA / clk / SM).  This is the kernel behind the framework's float64 arm — the
+// precision the reference runs end to end (experiments/dist_mnist_ex.py:19) — and replaces the batch-split generic
+// kernel (mnist_generic.cu) there, which streams the 221 KB fp64 W1 matrix three times per CTA.
+//
+// A node is `nsplit` clusters of 6 CTAs (MS = 64 / nsplit samples each); CTA c owns pooled rows {2c, 2c+1} of all three
+// channels = 72 of the 432 fc1 inputs for all MS samples: conv+ReLU+pool -> A_c [MS x 72]; H_c = A_c . W1_c^T reduced
+// over the cluster through distributed shared memory (reduce-scatter by samples, fc2 / loss / backward on the owners, dH
+// rows gathered back); da1_c = dH . W1_c and dW1_c = dH^T . A_c are local; dW1_c goes straight to its columns of the
+// gradient row; small gradients are reduced by rank 0 through DSMEM.  One gradient partial row per cluster.
+// GEMM tiling: a thread owns 2 rows x 4-5 strided columns; with rows padded to 73 / 65 doubles every operand read is
+// either a broadcast or conflict free, so the loops run at the DFMA rate.
+#include "mnist_device.cuh"
+
+namespace nndt {
+namespace mnist {
+
+namespace cl64 {
+
+constexpr int NT = 512, CL = 6, CELLS = 24, KC = 72, WS = 73, HS = 65;
+constexpr int PART_WC = 0, PART_BC = 75, PART_B1 = 78, PART_W2 = 142, PART_B2 = 782, PART_LOSS = 792, PART_N = 793;
+
+struct Smem {
+  double w[64 * WS];         // W1 slice [j][k], k = ch * 24 + cell; later da1 [s][72]
+  double a[64 * WS];         // A tile [s][k]
+  double dh[64 * HS];        // dH [s][j]
+  double hpart[64 * HS];     // partial H [s][j] (read by the peers)
+  float img[64 * 224];       // raw pixels of image rows 4c .. 4c+7 (u8 value or float value), [8][28] per sample
+  double h_loc[11 * 64];     // later the cross-warp scratch of the conv-grad reduction
+  double dh_loc[11 * 64];
+  double part[800];
+  double w2[NCLS * HID];
+  double b1[HID];
+  double b2[16];
+  double wc[80];
+  double z[11 * 16];
+  double dz[11 * 16];
+  double red[16];
+  int sidx[64];
+  int label[64];
+  float valid[64];
+  unsigned char arg[64 * KC];
+};
+static_assert(sizeof(Smem) <= 227 * 1024, "shared memory budget");
+
+NNDT_DEVINL void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+NNDT_DEVINL uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+NNDT_DEVINL uint32_t map_to(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(rank));
+  return r;
+}
+NNDT_DEVINL double ld_dsmem(uint32_t a) { double v; asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory"); return v; }
+NNDT_DEVINL double wsum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int MS>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1)
+mnist_cl64_train_kernel(const Args a, const GenericShape gs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int l = blockIdx.z, bsplit = blockIdx.y, nsplit = gridDim.y;
+  const int c = (int)cluster_rank();
+  const double* th = reinterpret_cast<const double*>(a.theta) + (size_t)l * a.n_pad;
+  auto own_lo = [](int r) { return (MS * r + CL - 1) / CL; };
+  const double pmean = gs.mean, pis = gs.inv_std;
+  const bool u8 = a.x_is_u8 != 0;
+
+  // ---- data half: sampler + image rows 4c .. 4c+7 (224 contiguous pixels per sample), before the PDL wait ---------------
+  const int call = a.calls != nullptr ? a.calls[l] : 0;
+  const BatchGeom bg = batch_geom<true>(a, l, call);
+  if (tid < MS) {
+    int idx = 0, lab = 0; float ok = 0.f;
+    const uint32_t t = (uint32_t)(bsplit * MS + tid);
+    if (t < bg.bs) {
+      ok = 1.f;
+      idx = a.direct ? (int)(l * a.batch + t) : bg.shard_off + (int)feistel_permute(bg.start + t, bg.m, bg.key);
+      lab = (int)a.y[idx];
+    }
+    sm.sidx[tid] = idx; sm.valid[tid] = ok; sm.label[tid] = lab;
+  }
+  __syncthreads();
+  constexpr int NU8 = (MS * 14 + NT - 1) / NT, NF4 = (MS * 56 + NT - 1) / NT;
+  uint4 pu[NU8]; float4 pf[NF4];
+  if (u8) {
+#pragma unroll
+    for (int i = 0; i < NU8; ++i) {
+      const int o = tid + i * NT;
+      pu[i] = make_uint4(0, 0, 0, 0);
+      if (o < MS * 14) {
+        const int s = o / 14, q = o - s * 14;
+        if (sm.valid[s] != 0.f)
+          pu[i] = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(a.x) + (size_t)sm.sidx[s] * 784 + 112 * c + 16 * q);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NF4; ++i) {
+      const int o = tid + i * NT;
+      pf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (o < MS * 56) {
+        const int s = o / 56, q = o - s * 56;
+        if (sm.valid[s] != 0.f)
+          pf[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.x) + (size_t)sm.sidx[s] * 784 + 112 * c + 4 * q);
+      }
+    }
+  }
+
+  pdl_wait();                 // the parameters of this step are final
+  pdl_launch_dependents();
+
+  // ---- W1 slice [64 j][72 k] (three 24-column runs per row), small tensors, pixels ---------------------------------------
+  for (int o = tid; o < HID * KC; o += NT) {
+    const int j = o / KC, r = o - j * KC, ch = r / CELLS, cell = r - ch * CELLS;
+    sm.w[j * WS + r] = __ldcg(th + a.off_w1 + (size_t)j * FC1_IN + ch * NPOOL + CELLS * c + cell);
+  }
+  for (int o = tid; o < NCLS * HID; o += NT) sm.w2[o] = __ldcg(th + a.off_w2 + o);
+  if (tid < 75) sm.wc[tid] = __ldcg(th + a.off_wc + tid);
+  else if (tid < 78) sm.wc[tid] = __ldcg(th + a.off_bc + (tid - 75));
+  else if (tid >= 96 && tid < 96 + HID) sm.b1[tid - 96] = __ldcg(th + a.off_b1 + (tid - 96));
+  else if (tid >= 160 && tid < 160 + NCLS) sm.b2[tid - 160] = __ldcg(th + a.off_b2 + (tid - 160));
+  if (u8) {
+#pragma unroll
+    for (int i = 0; i < NU8; ++i) {
+      const int o = tid + i * NT;
+      if (o < MS * 14) {
+        const int s = o / 14, q = o - s * 14;
+        const uint32_t w[4] = {pu[i].x, pu[i].y, pu[i].z, pu[i].w};
+        float* dst = sm.img + s * 224 + 16 * q;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dst[j] = (float)((w[j >> 2] >> (8 * (j & 3))) & 0xff);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NF4; ++i) {
+      const int o = tid + i * NT;
+      if (o < MS * 56) *reinterpret_cast<float4*>(sm.img + (o / 56) * 224 + 4 * (o % 56)) = pf[i];
+    }
+  }
+  __syncthreads();
+
+  // ---- conv + ReLU + maxpool: one (sample, pooled cell) per item, the 6x6 patch normalised to fp64 once -----------------
+  for (int it = tid; it < MS * CELLS; it += NT) {
+    const int s = it / CELLS, cell = it - s * CELLS;
+    const int pr = cell / PHW, px = cell - pr * PHW;
+    const float* src = sm.img + s * 224 + (2 * pr) * HW + 2 * px;
+    double patch[6][6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        const double v = (double)src[r * HW + q];
+        patch[r][q] = u8 ? (v * (1.0 / 255.0) - pmean) * pis : v;
+      }
+    const bool ok = sm.valid[s] != 0.f;
+#pragma unroll 1
+    for (int ch = 0; ch < F; ++ch) {
+      double a00 = 0, a01 = 0, a10 = 0, a11 = 0;
+#pragma unroll
+      for (int ky = 0; ky < KS; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx) {
+          const double w = sm.wc[ch * 25 + ky * 5 + kx];
+          a00 += w * patch[ky][kx]; a01 += w * patch[ky][kx + 1];
+          a10 += w * patch[ky + 1][kx]; a11 += w * patch[ky + 1][kx + 1];
+        }
+      double m = a00; int ai = 0;                      // first maximum wins, like ATen's max_pool2d
+      if (a01 > m) { m = a01; ai = 1; }
+      if (a10 > m) { m = a10; ai = 2; }
+      if (a11 > m) { m = a11; ai = 3; }
+      m += sm.wc[75 + ch];
+      m = (ok && m > 0.0) ? m : 0.0;
+      sm.a[s * WS + ch * CELLS + cell] = m;
+      sm.arg[s * KC + ch * CELLS + cell] = (unsigned char)(ai | (m > 0.0 ? 4 : 0));
+    }
+  }
+  __syncthreads();
+
+  // ---- GEMM 1: H_c[s][j] = sum_k A[s][k] W[j][k]; thread = rows {ts, ts+32} x columns {tj + 16 i} ------------------------
+  const int ts = tid >> 4, tj = tid & 15;
+  {
+    double acc[2][4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[r][i] = 0.0;
+    if (ts < MS) {
+      const double* a0 = sm.a + ts * WS;
+      const double* a1 = sm.a + (ts + 32 < MS ? ts + 32 : ts) * WS;
+#pragma unroll 4
+      for (int k = 0; k < KC; ++k) {
+        const double x0 = a0[k], x1 = a1[k];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const double wv = sm.w[(tj + 16 * i) * WS + k];
+          acc[0][i] += x0 * wv; acc[1][i] += x1 * wv;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        sm.hpart[ts * HS + tj + 16 * i] = acc[0][i];
+        if (ts + 32 < MS) sm.hpart[(ts + 32) * HS + tj + 16 * i] = acc[1][i];
+      }
+    }
+  }
+  cluster_sync();                                        // #1: all six partial H are in shared memory
+  if (c == 0 && tid == 0 && a.calls != nullptr) {
+    if (a.arrive == nullptr || nsplit == 1) a.calls[l] = call + 1;
+    else if (atomicAdd(a.arrive + l, 1u) == (unsigned)nsplit - 1) { a.arrive[l] = 0; a.calls[l] = call + 1; }
+  }
+
+  // ---- reduce-scatter of H + fc2 / loss / their backward for this CTA's samples --------------------------------------------
+  const int s0 = own_lo(c), ns = own_lo(c + 1) - s0;
+  const double inv_bs = 1.0 / (double)(bg.bs ? bg.bs : 1);
+  for (int o = tid; o < ns * HID; o += NT) {
+    const int sl = o >> 6, j = o & 63;
+    const double* src = sm.hpart + (s0 + sl) * HS + j;
+    double v = sm.b1[j];
+#pragma unroll
+    for (int r = 0; r < CL; ++r) v += ld_dsmem(map_to(src, (uint32_t)r));
+    sm.h_loc[o] = v > 0.0 ? v : 0.0;
+  }
+  __syncthreads();
+  {
+    const int o = tid >> 2, part = tid & 3;              // 4 lanes per logit
+    const bool live = o < ns * NCLS;
+    const int sl = live ? o / NCLS : 0, cc = live ? o - sl * NCLS : 0;
+    double v = 0.0;
+    if (live) {
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) { const int j = part * 16 + jj; v += sm.h_loc[sl * HID + j] * sm.w2[cc * HID + j]; }
+    }
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    if (live && part == 0) sm.z[sl * 16 + cc] = v + sm.b2[cc];
+  }
+  __syncthreads();
+  if (tid < ns) {
+    const int sl = tid, s = s0 + sl;
+    double mx = sm.z[sl * 16];
+#pragma unroll
+    for (int cc = 1; cc < NCLS; ++cc) mx = fmax(mx, sm.z[sl * 16 + cc]);
+    double se = 0.0;
+#pragma unroll
+    for (int cc = 0; cc < NCLS; ++cc) se += exp(sm.z[sl * 16 + cc] - mx);
+    const double lse = mx + log(se);
+    const int y = sm.label[s];
+    const double ok = (double)sm.valid[s];
+#pragma unroll
+    for (int cc = 0; cc < NCLS; ++cc)
+      sm.dz[sl * 16 + cc] = ok * inv_bs * (exp(sm.z[sl * 16 + cc] - lse) - (cc == y ? 1.0 : 0.0));
+    sm.red[sl] = ok * (lse - sm.z[sl * 16 + y]);
+  }
+  __syncthreads();
+  for (int o = tid; o < ns * HID; o += NT) {
+    const int sl = o >> 6, j = o & 63;
+    double v = 0.0;
+#pragma unroll
+    for (int cc = 0; cc < NCLS; ++cc) v += sm.dz[sl * 16 + cc] * sm.w2[cc * HID + j];
+    sm.dh_loc[o] = sm.h_loc[o] > 0.0 ? v : 0.0;
+  }
+  __syncthreads();
+  for (int o = tid; o < NCLS * HID; o += NT) {
+    const int cc = o >> 6, j = o & 63;
+    double v = 0.0;
+    for (int sl = 0; sl < ns; ++sl) v += sm.dz[sl * 16 + cc] * sm.h_loc[sl * HID + j];
+    sm.part[PART_W2 + o] = v;
+  }
+  if (tid < HID) {
+    double v = 0.0;
+    for (int sl = 0; sl < ns; ++sl) v += sm.dh_loc[sl * HID + tid];
+    sm.part[PART_B1 + tid] = v;
+  } else if (tid >= 64 && tid < 64 + NCLS) {
+    double v = 0.0;
+    for (int sl = 0; sl < ns; ++sl) v += sm.dz[sl * 16 + (tid - 64)];
+    sm.part[PART_B2 + (tid - 64)] = v;
+  } else if (tid == 96) {
+    double v = 0.0;
+    for (int sl = 0; sl < ns; ++sl) v += sm.red[sl];
+    sm.part[PART_LOSS] = v * inv_bs;
+  }
+  cluster_sync();                                        // #2: every owner's dH rows are final
+
+  // ---- gather all MS dH rows from their owners ------------------------------------------------------------------------------
+  for (int o = tid; o < MS * HID; o += NT) {
+    const int s = o >> 6, j = o & 63;
+    int r = 0;
+#pragma unroll
+    for (int q = 1; q < CL; ++q) r += (s >= own_lo(q)) ? 1 : 0;
+    sm.dh[s * HS + j] = ld_dsmem(map_to(sm.dh_loc + (s - own_lo(r)) * HID + j, (uint32_t)r));
+  }
+  __syncthreads();
+
+  // ---- GEMM 2: da1_c[s][k] = sum_j dH[s][j] W[j][k]; thread = rows {ts, ts+32} x columns {tj + 16 i}, i < 5 -------------
+  double d2[2][5];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int i = 0; i < 5; ++i) d2[r][i] = 0.0;
+  if (ts < MS) {
+    const double* h0 = sm.dh + ts * HS;
+    const double* h1 = sm.dh + (ts + 32 < MS ? ts + 32 : ts) * HS;
+#pragma unroll 4
+    for (int j = 0; j < HID; ++j) {
+      const double x0 = h0[j], x1 = h1[j];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const int k = tj + 16 * i;
+        const double wv = k < KC ? sm.w[j * WS + k] : 0.0;
+        d2[0][i] += x0 * wv; d2[1][i] += x1 * wv;
+      }
+    }
+  }
+  // ---- GEMM 3: dW1_c[j][k] = sum_s dH[s][j] A[s][k]; thread = rows (features) {ts, ts+32} x columns {tj + 16 i} -----------
+  double* gp = reinterpret_cast<double*>(a.grad_part) + ((size_t)l * nsplit + bsplit) * a.n_pad;
+  {
+    double d3[2][5];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int i = 0; i < 5; ++i) d3[r][i] = 0.0;
+#pragma unroll 2
+    for (int s = 0; s < MS; ++s) {
+      const double x0 = sm.dh[s * HS + ts], x1 = sm.dh[s * HS + ts + 32];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const int k = tj + 16 * i;
+        const double av = k < KC ? sm.a[s * WS + k] : 0.0;
+        d3[0][i] += x0 * av; d3[1][i] += x1 * av;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int k = tj + 16 * i;
+      if (k < KC) {
+        const int ch = k / CELLS, cell = k - ch * CELLS;
+        double* g = gp + a.off_w1 + ch * NPOOL + CELLS * c + cell;
+        g[(size_t)ts * FC1_IN] = d3[0][i];
+        g[(size_t)(ts + 32) * FC1_IN] = d3[1][i];
+      }
+    }
+  }
+  __syncthreads();      // every read of W (GEMM 2) is done: its rows become da1 [s][72], masked by ReLU'(a1)
+  double* da1 = sm.w;
+  if (ts < MS) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int k = tj + 16 * i;
+      if (k < KC) {
+        da1[ts * KC + k] = (sm.arg[ts * KC + k] & 4) ? d2[0][i] : 0.0;
+        if (ts + 32 < MS) da1[(ts + 32) * KC + k] = (sm.arg[(ts + 32) * KC + k] & 4) ? d2[1][i] : 0.0;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- conv grads, one channel at a time: each pooled cell routes da1 to its argmax conv position ---------------------------
+  double* wred = sm.h_loc;                                // [16 warps][26]
+#pragma unroll 1
+  for (int ch = 0; ch < F; ++ch) {
+    double cacc[26];
+#pragma unroll
+    for (int i = 0; i < 26; ++i) cacc[i] = 0.0;
+    for (int it = tid; it < MS * CELLS; it += NT) {
+      const int s = it / CELLS, cell = it - s * CELLS;
+      const double g = da1[s * KC + ch * CELLS + cell];
+      if (g != 0.0) {
+        const int ai = sm.arg[s * KC + ch * CELLS + cell] & 3;
+        const int pr = cell / PHW, px = cell - pr * PHW;
+        const float* src = sm.img + s * 224 + (2 * pr + (ai >> 1)) * HW + 2 * px + (ai & 1);
+#pragma unroll
+        for (int ky = 0; ky < KS; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < KS; ++kx) {
+            const double v = (double)src[ky * HW + kx];
+            cacc[ky * 5 + kx] += g * (u8 ? (v * (1.0 / 255.0) - pmean) * pis : v);
+          }
+        cacc[25] += g;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 26; ++i) {
+      const double v = wsum(cacc[i]);
+      if (lane == 0) wred[warp * 26 + i] = v;
+    }
+    __syncthreads();
+    if (tid < 26) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < NT / 32; ++w) v += wred[w * 26 + tid];
+      sm.part[tid < 25 ? PART_WC + ch * 25 + tid : PART_BC + ch] = v;
+    }
+    __syncthreads();
+  }
+  cluster_sync();                                        // #3: every CTA's share of the small gradients is in `part`
+  if (c == 0) {
+    for (int o = tid; o < PART_N; o += NT) {
+      double v = 0.0;
+#pragma unroll
+      for (int r = 0; r < CL; ++r) v += ld_dsmem(map_to(sm.part + o, (uint32_t)r));
+      if (o < PART_BC) gp[a.off_wc + o] = v;
+      else if (o < PART_B1) gp[a.off_bc + (o - PART_BC)] = v;
+      else if (o < PART_W2) gp[a.off_b1 + (o - PART_B1)] = v;
+      else if (o < PART_B2) gp[a.off_w2 + (o - PART_W2)] = v;
+      else if (o < PART_LOSS) gp[a.off_b2 + (o - PART_B2)] = v;
+      else {
+        a.loss_part[l * nsplit + bsplit] = (float)v;
+        if (a.loss_mirror != nullptr) a.loss_mirror[l * nsplit + bsplit] = (float)v;
+      }
+    }
+  }
+  cluster_sync();                                        // #4: rank 0 is done reading the peers' shared memory
+}
+
+template <int MS>
+static cudaError_t launch_ms(const Args& a, const GenericShape& gs, cudaStream_t st) {
+  static cudaError_t prep = cudaFuncSetAttribute(mnist_cl64_train_kernel<MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+  if (prep != cudaSuccess) return prep;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(CL, 64 / MS, a.L); cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = sizeof(Smem); cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  static const bool no_pdl = getenv("NNDT_NO_PDL") != nullptr;
+  cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, mnist_cl64_train_kernel<MS>, a, gs);
+}
+
+}  // namespace cl64
+
+cudaError_t launch_train_cl64(const Args& a, const GenericShape& gs, int nsplit, cudaStream_t st) {
+  switch (nsplit) {
+    case 1: return cl64::launch_ms<64>(a, gs, st);
+    case 2: return cl64::launch_ms<32>(a, gs, st);
+    case 4: return cl64::launch_ms<16>(a, gs, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+int cl64_max_active_clusters() {
+  if (cudaFuncSetAttribute(cl64::mnist_cl64_train_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(cl64::Smem)) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(cl64::CL, 1, 1); cfg.blockDim = dim3(cl64::NT); cfg.dynamicSmemBytes = sizeof(cl64::Smem);
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, cl64::mnist_cl64_train_kernel<64>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+}  // namespace mnist
+}  // namespace nndt

@@ -60,7 +60,15 @@ class FusedMnist:
             # 6 * nsplit * L CTAs in one wave — the conv / conv-grad phases are CUDA-core work that scales with SMs
             want = int(os.environ.get("NNDT_TC_SPLIT", "0"))
             self.S = want if want in (1, 2, 4) else max([n for n in (1, 2, 4) if 6 * n * self.L <= sms] or [1])
-        self.kernel_name = (f"mnist_tc_train_kernel<{64 // self.S}> (tcgen05 kind::tf32 3xTF32, TMEM, TMA tensor map, {self.S} x 6-CTA cluster per node)" if self.tc
+        # float64, paper shape, batch <= 64: the same K-split cluster decomposition on the fp64 CUDA cores (csrc/mnist_cl64.cu);
+        # NNDT_MNIST_CL64=0 keeps the batch-split generic kernel (A/B)
+        self.cl64 = (self.generic and self.dtype == torch.float64 and mnist_kernel_is_paper_shape(spec) and self.B <= 64
+                     and os.environ.get("NNDT_MNIST_CL64", "1") != "0" and self.ext.mnist_cl64_max_clusters() >= 1)
+        if self.cl64:
+            want = int(os.environ.get("NNDT_TC_SPLIT", "0"))
+            self.S = want if want in (1, 2, 4) else max([n for n in (1, 2, 4) if 6 * n * self.L <= sms] or [1])
+        self.kernel_name = (f"mnist_cl64_train_kernel<{64 // self.S}> (fp64 CUDA cores, {self.S} x 6-CTA cluster per node, DSMEM reduce)" if self.cl64 else
+                            f"mnist_tc_train_kernel<{64 // self.S}> (tcgen05 kind::tf32 3xTF32, TMEM, TMA tensor map, {self.S} x 6-CTA cluster per node)" if self.tc
                             else "convnet_generic_kernel (CUDA cores)" if self.generic else "mnist_kernel (mma.sync 3xTF32)")
         sh = problem.shards
         self.x = sh.x.reshape(sh.x.shape[0], -1).contiguous()
@@ -91,7 +99,7 @@ class FusedMnist:
             grad_part=self.grad_part.data_ptr(), loss_part=self.loss_part.data_ptr(),
             spb=self.spb, S=self.S, tune=int(os.environ.get("NNDT_MNIST_TUNE", "1")),
             generic=int(self.generic), num_filters=spec.num_filters, kernel_size=spec.kernel_size,
-            linear_width=spec.linear_width, dtype64=int(self.dtype == torch.float64))
+            linear_width=spec.linear_width, dtype64=int(self.dtype == torch.float64), cl64=int(self.cl64))
         if self.tc:
             self.base.update(tc=1, w1_map=self.ext.make_w1_tensor_map(a.theta.data_ptr(), a.n_pad, self.L, off[names[2]]))
         if os.environ.get("NNDT_STEP_PROF") == "1":     # scripts/profile_round_phases.py --per-step
@@ -225,7 +233,7 @@ class FusedMnist:
         # a training CTA fills an SM's register file (768 threads x 80 registers): a staging block that lands on
         # an SM evicts a training CTA into a second wave, so the staging grid is sized to the SMs left over
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        ctas = self.L * self.S * (6 if self.tc else 1)
+        ctas = self.L * self.S * (6 if (self.tc or self.cl64) else 1)
         free = sms - ctas if ctas <= sms else 0      # multi-wave grids leave no SM idle
         gather_blocks = int(os.environ.get("NNDT_GATHER_BLOCKS", "0")) or max(8, min(24, free - 2))
         self.direct_ops, self.gather_ops = [], []

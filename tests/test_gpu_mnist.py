@@ -377,3 +377,23 @@ def test_tc_kernel_matches_batch_split_kernel_and_autograd(B, float_inputs, monk
         _assert_grads_close(tc.arena.grad, ref.arena.grad)
         _assert_grads_close(tc.arena.grad, old.arena.grad)
     assert (tc.calls == ref.calls).all()
+
+
+@pytest.mark.parametrize("B", [64, 37, 8])
+def test_fp64_cluster_kernel_matches_generic_kernel_and_autograd(B, monkeypatch):
+    """csrc/mnist_cl64.cu (K-split cluster kernel, the float64 arm of the paper shape) against the batch-split generic
+    fp64 kernel (NNDT_MNIST_CL64=0) and PyTorch autograd in float64."""
+    cl = _generic_problem((3, 5, 64), torch.float64, "fused", B=B)
+    monkeypatch.setenv("NNDT_MNIST_CL64", "0")
+    gen = _generic_problem((3, 5, 64), torch.float64, "fused", B=B)
+    monkeypatch.delenv("NNDT_MNIST_CL64")
+    ref = _generic_problem((3, 5, 64), torch.float64, "torch", B=B)
+    assert cl.fused.cl64 and not gen.fused.cl64
+    gen.arena.theta.copy_(cl.arena.theta)
+    ref.arena.theta.copy_(cl.arena.theta)
+    for step in range(4):
+        lc, lg, lr = cl.compute_grads().clone(), gen.compute_grads().clone(), ref.compute_grads().clone()
+        torch.testing.assert_close(lc, lr, rtol=1e-6, atol=1e-7)
+        torch.testing.assert_close(cl.arena.grad, ref.arena.grad, rtol=1e-9, atol=1e-11)
+        torch.testing.assert_close(cl.arena.grad, gen.arena.grad, rtol=1e-9, atol=1e-11)
+    assert (cl.calls == ref.calls).all()
