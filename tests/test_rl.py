@@ -200,3 +200,21 @@ def test_train_script_cli_writes_the_artefacts(tmp_path):
             "agreements_dsgd_3.npz", "dsgd_3_0.gif"} <= files
     s = plot_reward.summarize(out)
     assert s["dsgd"]["runs"] == 1
+
+
+def test_shipped_dinno_ppo_policies_catch_the_prey():
+    """R10: the trained artefacts shipped under rl/trained (reference file names) load through the evaluation tool and the
+    DiNNO-PPO predators score far above the untrained plateau (-90) — see profiles/rl_rewards.md."""
+    import os
+    import numpy as np
+    from nn_distributed_training_b200.rl.eval_policy import load_distributed_actors, rollout
+    from nn_distributed_training_b200.rl.model import FFReLUNet
+    from nn_distributed_training_b200.rl.simple_tag import SimpleTagEnv
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "nn_distributed_training_b200", "rl", "trained")
+    curve = np.load(os.path.join(d, "avg_ep_rews_dinno_0.npy"))
+    assert curve[:10].mean() < -50 and curve[-50:].mean() > 380          # the reference's DiNNO-PPO ends at 380-498
+    assert np.load(os.path.join(d, "avg_ep_rews_dsgd_0.npy"))[-50:].mean() < 0      # DSGD-PPO never learns (as in the reference)
+    env = SimpleTagEnv(num_envs=16, num_good=1, num_adversaries=3, num_obstacles=8, max_cycles=50, device="cpu", seed=5)
+    actors = load_distributed_actors(os.path.join(d, "ppo_actors_tag_dinno_0_3000.pth"), lambda: FFReLUNet([12, 64, 64, 64, 5]), 3)
+    ret, length, _ = rollout(actors, env)
+    assert length == 50 and ret.mean() > 300
