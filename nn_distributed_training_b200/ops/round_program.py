@@ -81,7 +81,7 @@ class RoundProgram:
         pipeline = "resident"
         if pr.fused is not None:
             pipeline = pr.conf.get("input_pipeline", "auto")
-            can_stage = hasattr(pr.fused, "enable_host_feed") and self.capturable and not init_draws
+            can_stage = hasattr(pr.fused, "enable_host_feed") and self.capturable
             if pipeline == "auto":
                 # staged-resident is the faster way to run resident shards (4 % on the headline round): the training
                 # kernel reads a compact, L2-resident batch instead of chasing the sampler through HBM
@@ -102,20 +102,14 @@ class RoundProgram:
         self._pub_pending = False
         if pr.fused is not None:
             pr.fused.sync_calls_from_host()
+            self._deferred_pipeline = None
             if pipeline in ("host", "staged") and hasattr(pr.fused, "enable_host_feed"):
                 if init_draws:
-                    raise NotImplementedError("host-fed / staged pipeline with DSGT init_grads")
-                pr.fused.enable_host_feed(self.dpr, nslots=int(pr.conf.get("host_slots", 4)),
-                                          threads=int(pr.conf.get("host_threads", 4)),
-                                          mode="staged" if pipeline == "staged" else pr.conf.get("host_gather", "gpu_pull"))
-                self.host_mode = True
-                self.pipeline = pipeline
-                self._runner = None
-                self._stage_set = 0
-                self._pull_graphs: Dict = {}
-                self._pull_parity = 0
-                self._pull_primed = False
-                self._side = None
+                    # DSGT init_grads (optimizers/dsgt.py:33-46 of the reference): the ONE initial gradient draw runs on the
+                    # resident shards; the host-fed / staged stream starts at the draw after it (dsgt_init switches over)
+                    self._deferred_pipeline = pipeline
+                else:
+                    self._enable_pipeline(pipeline)
             # opt-in: measured slower than the PDL-overlapped per-step kernels (docs/perf_notes.md), kept as the
             # in-kernel phase profiler (scripts/profile_round_phases.py) and for launch-bound environments
             want = pr.conf.get("fused_round", opt.conf.get("fused_round", False)) or os.environ.get("NNDT_FUSED_ROUND") == "1"
@@ -123,6 +117,20 @@ class RoundProgram:
                     and getattr(pr.fused, "supports_round_kernel", lambda o: False)(opt)):
                 sets = [0, 1] if self.host_mode else [None]
                 self._round_ops = {b: pr.fused.round_op(self.eng._keep, b) for b in sets}
+
+    def _enable_pipeline(self, pipeline: str):
+        pr = self.pr
+        pr.fused.enable_host_feed(self.dpr, nslots=int(pr.conf.get("host_slots", 4)),
+                                  threads=int(pr.conf.get("host_threads", 4)),
+                                  mode="staged" if pipeline == "staged" else pr.conf.get("host_gather", "gpu_pull"))
+        self.host_mode = True
+        self.pipeline = pipeline
+        self._runner = None
+        self._stage_set = 0
+        self._pull_graphs: Dict = {}
+        self._pull_parity = 0
+        self._pull_primed = False
+        self._side = None
 
     # ---- peer announcement off the critical path ---------------------------------------------------------------
     def _publish_forked(self):
@@ -177,6 +185,10 @@ class RoundProgram:
         self.eng.op.dsgt_init()
         if self.pr.fused is not None:
             self.pr.count_draws_all(1)
+            if getattr(self, "_deferred_pipeline", None):
+                torch.cuda.synchronize(self.pr.device)      # the kernel-owned draw counters have advanced
+                self._enable_pipeline(self._deferred_pipeline)
+                self._deferred_pipeline = None
 
     def _capture_pull_graph(self, R: int, parity: int):
         """``R`` host-fed rounds as ONE graph with two branches: while round i computes on the capture stream,

@@ -113,8 +113,6 @@ def main():
         return delayed(ctx, N, G, backend)
     ok = True
     for alg, conf in CONFS.items():
-        if args.pipeline == "host" and alg == "dsgt":
-            continue                    # host-fed DSGT with init_grads is not implemented (round_program.py)
         pr = build(ctx, N, G, conf, backend, pipeline=args.pipeline)
         opt = build_optimizer(pr, ctx.device, copy.deepcopy(conf))
         opt.train()

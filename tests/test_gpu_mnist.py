@@ -205,6 +205,27 @@ def test_host_fed_pipeline_matches_resident(mode):
     assert outs[0][1] == outs[1][1] and (outs[0][2] == outs[1][2]).all()
 
 
+@pytest.mark.parametrize("pipeline", ["staged", "host"])
+def test_dsgt_init_grads_with_host_fed_and_staged_pipelines(pipeline):
+    """The paper's DSGT config (init_grads: true) through the host-fed / staged input pipelines: the one initial
+    gradient draw runs on the resident shards, the stream takes over at the next draw — identical to the resident run."""
+    outs = []
+    for pl in ("resident", pipeline):
+        conf = dict(DSGT_C, outer_iterations=12)
+        pr = _problem(4, 32, "fused", conf, M=100, eval_every=1000)
+        pr.conf["input_pipeline"] = pl
+        opt = DSGT(pr, DEV, conf)
+        opt.run_rounds(5)
+        opt.run_rounds(4)
+        torch.cuda.synchronize()
+        assert opt._program.pipeline == pl
+        outs.append((pr.arena.theta.clone(), pr.forward_cnt, pr.calls.copy()))
+        if pr.fused.host_feed is not None and pr.fused.loader is not None:
+            pr.fused.loader.stop()
+    torch.testing.assert_close(outs[0][0], outs[1][0], rtol=0, atol=0)
+    assert outs[0][1] == outs[1][1] and (outs[0][2] == outs[1][2]).all()
+
+
 def test_fused_consensus_metric_matches_torch():
     """The fused metric kernel (used at evaluation points of fused runs) vs the torch normalize/cdist oracle."""
     from nn_distributed_training_b200.ops import consensus_ref
