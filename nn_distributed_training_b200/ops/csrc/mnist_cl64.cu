@@ -60,6 +60,14 @@ NNDT_DEVINL double wsum(double v) {
   return v;
 }
 
+NNDT_DEVINL void stamp(long long* prof, int idx, int tid) {
+  if (prof != nullptr && tid == 0) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    prof[idx] = t;
+  }
+}
+
 template <int MS>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1)
 mnist_cl64_train_kernel(const Args a, const GenericShape gs) {
@@ -72,6 +80,8 @@ mnist_cl64_train_kernel(const Args a, const GenericShape gs) {
   auto own_lo = [](int r) { return (MS * r + CL - 1) / CL; };
   const double pmean = gs.mean, pis = gs.inv_std;
   const bool u8 = a.x_is_u8 != 0;
+  long long* prof = a.prof != nullptr ? a.prof + ((l * nsplit + bsplit) * CL + c) * 64 : nullptr;
+  stamp(prof, 0, tid);
 
   // ---- data half: sampler + image rows 4c .. 4c+7 (224 contiguous pixels per sample), before the PDL wait ---------------
   const int call = a.calls != nullptr ? a.calls[l] : 0;
@@ -113,8 +123,10 @@ mnist_cl64_train_kernel(const Args a, const GenericShape gs) {
     }
   }
 
+  stamp(prof, 1, tid);
   pdl_wait();                 // the parameters of this step are final
   pdl_launch_dependents();
+  stamp(prof, 2, tid);
 
   // ---- W1 slice [64 j][72 k] (three 24-column runs per row), small tensors, pixels ---------------------------------------
   for (int o = tid; o < HID * KC; o += NT) {
@@ -146,6 +158,7 @@ mnist_cl64_train_kernel(const Args a, const GenericShape gs) {
     }
   }
   __syncthreads();
+  stamp(prof, 3, tid);
 
   // ---- conv + ReLU + maxpool: one (sample, pooled cell) per item, the 6x6 patch normalised to fp64 once -----------------
   for (int it = tid; it < MS * CELLS; it += NT) {
@@ -184,34 +197,38 @@ mnist_cl64_train_kernel(const Args a, const GenericShape gs) {
   }
   __syncthreads();
 
-  // ---- GEMM 1: H_c[s][j] = sum_k A[s][k] W[j][k]; thread = rows {ts, ts+32} x columns {tj + 16 i} ------------------------
-  const int ts = tid >> 4, tj = tid & 15;
-  {
-    double acc[2][4];
+  stamp(prof, 4, tid);
+  // ---- GEMM 1: H_c[s][j] = sum_k A[s][k] W[j][k].  Register tile 4 rows x 4 columns (rows tr + RQ i, columns tc + 16 i):
+  //      per k a warp issues 4 + 4 shared-memory wavefronts for 16 DFMA instructions, which balances the 128 B/clk of shared
+  //      memory against the 64 DFMA/clk of the SM; MS * 4 threads are busy.
+  constexpr int RQ = MS / 4;                              // row-group count; thread t < MS * 4
+  const int tr = tid >> 4, tc = tid & 15;
+  if (tid < MS * 4) {
+    double acc[4][4];
 #pragma unroll
-    for (int r = 0; r < 2; ++r)
+    for (int r = 0; r < 4; ++r)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[r][i] = 0.0;
-    if (ts < MS) {
-      const double* a0 = sm.a + ts * WS;
-      const double* a1 = sm.a + (ts + 32 < MS ? ts + 32 : ts) * WS;
-#pragma unroll 4
-      for (int k = 0; k < KC; ++k) {
-        const double x0 = a0[k], x1 = a1[k];
+#pragma unroll 2
+    for (int k = 0; k < KC; ++k) {
+      double x[4], wv[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const double wv = sm.w[(tj + 16 * i) * WS + k];
-          acc[0][i] += x0 * wv; acc[1][i] += x1 * wv;
-        }
-      }
+      for (int r = 0; r < 4; ++r) x[r] = sm.a[(tr + RQ * r) * WS + k];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        sm.hpart[ts * HS + tj + 16 * i] = acc[0][i];
-        if (ts + 32 < MS) sm.hpart[(ts + 32) * HS + tj + 16 * i] = acc[1][i];
-      }
+      for (int i = 0; i < 4; ++i) wv[i] = sm.w[(tc + 16 * i) * WS + k];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[r][i] += x[r] * wv[i];
     }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sm.hpart[(tr + RQ * r) * HS + tc + 16 * i] = acc[r][i];
   }
+  stamp(prof, 5, tid);
   cluster_sync();                                        // #1: all six partial H are in shared memory
+  stamp(prof, 6, tid);
   if (c == 0 && tid == 0 && a.calls != nullptr) {
     if (a.arrive == nullptr || nsplit == 1) a.calls[l] = call + 1;
     else if (atomicAdd(a.arrive + l, 1u) == (unsigned)nsplit - 1) { a.arrive[l] = 0; a.calls[l] = call + 1; }
@@ -287,7 +304,9 @@ mnist_cl64_train_kernel(const Args a, const GenericShape gs) {
     for (int sl = 0; sl < ns; ++sl) v += sm.red[sl];
     sm.part[PART_LOSS] = v * inv_bs;
   }
+  stamp(prof, 7, tid);
   cluster_sync();                                        // #2: every owner's dH rows are final
+  stamp(prof, 8, tid);
 
   // ---- gather all MS dH rows from their owners ------------------------------------------------------------------------------
   for (int o = tid; o < MS * HID; o += NT) {
@@ -299,70 +318,76 @@ mnist_cl64_train_kernel(const Args a, const GenericShape gs) {
   }
   __syncthreads();
 
-  // ---- GEMM 2: da1_c[s][k] = sum_j dH[s][j] W[j][k]; thread = rows {ts, ts+32} x columns {tj + 16 i}, i < 5 -------------
-  double d2[2][5];
+  stamp(prof, 9, tid);
+  // ---- GEMM 2: da1_c[s][k] = sum_j dH[s][j] W[j][k]; tile 4 rows x 5 columns (k = tc + 16 i < 72) -------------------------
+  double d2[4][5];
 #pragma unroll
-  for (int r = 0; r < 2; ++r)
+  for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int i = 0; i < 5; ++i) d2[r][i] = 0.0;
-  if (ts < MS) {
-    const double* h0 = sm.dh + ts * HS;
-    const double* h1 = sm.dh + (ts + 32 < MS ? ts + 32 : ts) * HS;
-#pragma unroll 4
+  if (tid < MS * 4) {
+#pragma unroll 2
     for (int j = 0; j < HID; ++j) {
-      const double x0 = h0[j], x1 = h1[j];
+      double x[4], wv[5];
 #pragma unroll
-      for (int i = 0; i < 5; ++i) {
-        const int k = tj + 16 * i;
-        const double wv = k < KC ? sm.w[j * WS + k] : 0.0;
-        d2[0][i] += x0 * wv; d2[1][i] += x1 * wv;
-      }
+      for (int r = 0; r < 4; ++r) x[r] = sm.dh[(tr + RQ * r) * HS + j];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) wv[i] = (tc + 16 * i < KC) ? sm.w[j * WS + tc + 16 * i] : 0.0;
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int i = 0; i < 5; ++i) d2[r][i] += x[r] * wv[i];
     }
   }
-  // ---- GEMM 3: dW1_c[j][k] = sum_s dH[s][j] A[s][k]; thread = rows (features) {ts, ts+32} x columns {tj + 16 i} -----------
+  stamp(prof, 10, tid);
+  // ---- GEMM 3: dW1_c[j][k] = sum_s dH[s][j] A[s][k]; tile 4 features (tr + 16 r, tr < 16) x 5 columns; 256 threads --------
   double* gp = reinterpret_cast<double*>(a.grad_part) + ((size_t)l * nsplit + bsplit) * a.n_pad;
-  {
-    double d3[2][5];
+  if (tid < 256) {
+    double d3[4][5];
 #pragma unroll
-    for (int r = 0; r < 2; ++r)
+    for (int r = 0; r < 4; ++r)
 #pragma unroll
       for (int i = 0; i < 5; ++i) d3[r][i] = 0.0;
 #pragma unroll 2
     for (int s = 0; s < MS; ++s) {
-      const double x0 = sm.dh[s * HS + ts], x1 = sm.dh[s * HS + ts + 32];
+      double x[4], av[5];
 #pragma unroll
-      for (int i = 0; i < 5; ++i) {
-        const int k = tj + 16 * i;
-        const double av = k < KC ? sm.a[s * WS + k] : 0.0;
-        d3[0][i] += x0 * av; d3[1][i] += x1 * av;
-      }
+      for (int r = 0; r < 4; ++r) x[r] = sm.dh[s * HS + tr + 16 * r];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) av[i] = (tc + 16 * i < KC) ? sm.a[s * WS + tc + 16 * i] : 0.0;
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int i = 0; i < 5; ++i) d3[r][i] += x[r] * av[i];
     }
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
-      const int k = tj + 16 * i;
+      const int k = tc + 16 * i;
       if (k < KC) {
         const int ch = k / CELLS, cell = k - ch * CELLS;
         double* g = gp + a.off_w1 + ch * NPOOL + CELLS * c + cell;
-        g[(size_t)ts * FC1_IN] = d3[0][i];
-        g[(size_t)(ts + 32) * FC1_IN] = d3[1][i];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) g[(size_t)(tr + 16 * r) * FC1_IN] = d3[r][i];
       }
     }
   }
-  __syncthreads();      // every read of W (GEMM 2) is done: its rows become da1 [s][72], masked by ReLU'(a1)
-  double* da1 = sm.w;
-  if (ts < MS) {
+  __syncthreads();      // every read of W (GEMM 2) and of A / dH (GEMM 3) is done
+  stamp(prof, 11, tid);
+  double* da1 = sm.w;   // W's rows become da1 [s][72], masked by ReLU'(a1)
+  if (tid < MS * 4) {
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      const int k = tj + 16 * i;
-      if (k < KC) {
-        da1[ts * KC + k] = (sm.arg[ts * KC + k] & 4) ? d2[0][i] : 0.0;
-        if (ts + 32 < MS) da1[(ts + 32) * KC + k] = (sm.arg[(ts + 32) * KC + k] & 4) ? d2[1][i] : 0.0;
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const int s = tr + RQ * r, k = tc + 16 * i;
+        if (k < KC) da1[s * KC + k] = (sm.arg[s * KC + k] & 4) ? d2[r][i] : 0.0;
       }
-    }
   }
   __syncthreads();
-  // ---- conv grads, one channel at a time: each pooled cell routes da1 to its argmax conv position ---------------------------
-  double* wred = sm.h_loc;                                // [16 warps][26]
+  // ---- conv grads, one channel at a time: each pooled cell routes da1 to its argmax conv position; the per-thread sums
+  //      are folded over lane pairs and transposed through the dead A / dH tiles ([26][256] doubles) -----------------------------
+  double* scratch = sm.a;
+  static_assert(sizeof(double) * 26 * (NT / 2) <= sizeof(double) * (64 * WS + 64 * HS), "conv-grad scratch fits A + dH");
 #pragma unroll 1
   for (int ch = 0; ch < F; ++ch) {
     double cacc[26];
@@ -387,18 +412,20 @@ mnist_cl64_train_kernel(const Args a, const GenericShape gs) {
     }
 #pragma unroll
     for (int i = 0; i < 26; ++i) {
-      const double v = wsum(cacc[i]);
-      if (lane == 0) wred[warp * 26 + i] = v;
+      const double v = cacc[i] + __shfl_xor_sync(0xffffffffu, cacc[i], 1);
+      if ((lane & 1) == 0) scratch[i * (NT / 2) + (tid >> 1)] = v;
     }
     __syncthreads();
-    if (tid < 26) {
+    for (int o = warp; o < 26; o += NT / 32) {
       double v = 0.0;
 #pragma unroll
-      for (int w = 0; w < NT / 32; ++w) v += wred[w * 26 + tid];
-      sm.part[tid < 25 ? PART_WC + ch * 25 + tid : PART_BC + ch] = v;
+      for (int q = 0; q < NT / 64; ++q) v += scratch[o * (NT / 2) + lane + 32 * q];
+      v = wsum(v);
+      if (lane == 0) sm.part[o < 25 ? PART_WC + ch * 25 + o : PART_BC + ch] = v;
     }
     __syncthreads();
   }
+  stamp(prof, 12, tid);
   cluster_sync();                                        // #3: every CTA's share of the small gradients is in `part`
   if (c == 0) {
     for (int o = tid; o < PART_N; o += NT) {
@@ -417,6 +444,7 @@ mnist_cl64_train_kernel(const Args a, const GenericShape gs) {
     }
   }
   cluster_sync();                                        // #4: rank 0 is done reading the peers' shared memory
+  stamp(prof, 13, tid);
 }
 
 template <int MS>

@@ -46,7 +46,8 @@ struct Smem {
   float hpart[64 * KC];                          // partial H [64][65] (read by the peers), later da1 [64][72]
   float h_loc[11 * 64];
   float dh_loc[11 * 64];
-  float part[800];                               // this CTA's share of the small gradients + loss (read by rank 0)
+  float part[800];                               // this CTA's share of the fc2 / b1 gradients + loss (read by the peers)
+  float cpart[CL * 80];                          // rank 0: the six CTAs' conv-gradient shares (written by the peers)
   float w2[NCLS * HID];
   float b1[HID];
   float b2[16];
@@ -246,7 +247,8 @@ mnist_tc_train_kernel(const Args a, const __grid_constant__ CUtensorMap w1_map) 
     unsigned char* base = (buf ? sm.a_lo : sm.a_hi) + ch * SLAB;
     *reinterpret_cast<float4*>(base + umma::swz_chunk_off(row, chunk)) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  // pixels -> normalised fp32 in even/odd column planes
+  // pixels -> normalised fp32 in even/odd column planes.  A sample's 8 x 28 slab is contiguous and 28 is even, so pixel p
+  // lands at plane index p / 2: a run of 16 pixels is two aligned runs of 8 floats (vector stores)
   if (a.x_is_u8) {
 #pragma unroll
     for (int i = 0; i < NU8; ++i) {
@@ -255,14 +257,16 @@ mnist_tc_train_kernel(const Args a, const __grid_constant__ CUtensorMap w1_map) 
         const int s = o / 14, q = o - s * 14;
         const bool ok = sm.valid[s] != 0.f;
         const uint32_t w[4] = {pu[i].x, pu[i].y, pu[i].z, pu[i].w};
-        int row = (16 * q) / HW, col = 16 * q - row * HW;          // 16 consecutive pixels; a row has 28
-        float* xe = sm.xe + s * XP; float* xo = sm.xo + s * XP;
+        float ev[8], od[8];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float v = ok ? (((w[j >> 2] >> (8 * (j & 3))) & 0xff) * (1.f / 255.f) - a.mean) * a.inv_std : 0.f;
-          ((col & 1) ? xo : xe)[row * 14 + (col >> 1)] = v;
-          if (++col == HW) { col = 0; ++row; }
+          if (j & 1) od[j >> 1] = v; else ev[j >> 1] = v;
         }
+        float4* de = reinterpret_cast<float4*>(sm.xe + s * XP + 8 * q);
+        float4* dd = reinterpret_cast<float4*>(sm.xo + s * XP + 8 * q);
+        de[0] = make_float4(ev[0], ev[1], ev[2], ev[3]); de[1] = make_float4(ev[4], ev[5], ev[6], ev[7]);
+        dd[0] = make_float4(od[0], od[1], od[2], od[3]); dd[1] = make_float4(od[4], od[5], od[6], od[7]);
       }
     }
   } else {
@@ -271,10 +275,8 @@ mnist_tc_train_kernel(const Args a, const __grid_constant__ CUtensorMap w1_map) 
       const int o = tid + i * NT;
       if (o < MS * 56) {
         const int s = o / 56, q = o - s * 56;
-        const float v[4] = {pf[i].x, pf[i].y, pf[i].z, pf[i].w};
-        const int row = (4 * q) / HW, col = 4 * q - row * HW;      // 28 = 7 x 4: a float4 never straddles a row
-#pragma unroll
-        for (int j = 0; j < 4; ++j) (((col + j) & 1) ? sm.xo : sm.xe)[s * XP + row * 14 + ((col + j) >> 1)] = v[j];
+        *reinterpret_cast<float2*>(sm.xe + s * XP + 2 * q) = make_float2(pf[i].x, pf[i].z);
+        *reinterpret_cast<float2*>(sm.xo + s * XP + 2 * q) = make_float2(pf[i].y, pf[i].w);
       }
     }
   }
@@ -448,6 +450,25 @@ mnist_tc_train_kernel(const Args a, const __grid_constant__ CUtensorMap w1_map) 
   stamp(prof, 7, tid);
   cluster_sync();                                        // #2: every owner's dH rows are final; hpart is free again
   stamp(prof, 8, tid);
+  float* gp = a.grad_part + ((size_t)l * nsplit + bsplit) * a.n_pad;
+  // the fc2 / b1 / loss shares of all six CTAs are final: CTA c reduces its sixth of them (DSMEM reads) and writes the
+  // result; the peers stay resident until the last cluster barrier, so nothing else has to wait for this
+  {
+    constexpr int NE = PART_N - PART_B1, PER = (NE + CL - 1) / CL;          // 715 values
+    const int o = PART_B1 + c * PER + tid;
+    if (tid < PER && o < PART_N) {
+      float v = 0.f;
+#pragma unroll
+      for (int r = 0; r < CL; ++r) v += ld_dsmem(map_to(sm.part + o, (uint32_t)r));
+      if (o < PART_W2) gp[a.off_b1 + (o - PART_B1)] = v;
+      else if (o < PART_B2) gp[a.off_w2 + (o - PART_W2)] = v;
+      else if (o < PART_LOSS) gp[a.off_b2 + (o - PART_B2)] = v;
+      else {
+        a.loss_part[l * nsplit + bsplit] = v;
+        if (a.loss_mirror != nullptr) a.loss_mirror[l * nsplit + bsplit] = v;     // zero-copy store to pinned host memory
+      }
+    }
+  }
 
   // ---- gather all MS dH rows from their owners (DSMEM reads) into the local K-major operand tile (hi / lo), and
   //      re-swizzle the W1 slice for its MN-major use (W is dead as a K-major operand: MMA 1 has completed) -------------
@@ -508,7 +529,6 @@ mnist_tc_train_kernel(const Args a, const __grid_constant__ CUtensorMap w1_map) 
     }
     umma::commit(&sm.bar_m3);
   }
-  float* gp = a.grad_part + ((size_t)l * nsplit + bsplit) * a.n_pad;
   // 24 warps: TMEM quarter q, 16 accumulator columns each: channel atom ch, half of its 32 columns
   const int eq = warp & 3, esub = warp >> 2, ech = esub >> 1, ehalf = esub & 1;
   const int erow = 16 * eq + lane;                       // valid for lane < 16
@@ -531,23 +551,10 @@ mnist_tc_train_kernel(const Args a, const __grid_constant__ CUtensorMap w1_map) 
       }
     }
   }
-  umma::mbar_wait(&sm.bar_m3, 0);
-  umma::fence_after_sync();
+  __syncthreads();        // da1 complete
   stamp(prof, 11, tid);
-  {
-    float v3[16];
-    umma::tmem_ld16(tmem + ((uint32_t)(32 * eq) << 16) + TM_D3 + 32 * ech + 16 * ehalf, v3);
-    if (lane < 16) {
-      float* gw = gp + a.off_w1 + erow * FC1_IN + ech * NPOOL + CELLS * c + 16 * ehalf;
-#pragma unroll
-      for (int i = 0; i < 16; i += 4)
-        if (i < nvalid) *reinterpret_cast<float4*>(gw + i) = make_float4(v3[i], v3[i + 1], v3[i + 2], v3[i + 3]);
-    }
-  }
-  umma::fence_before_sync();
-  __syncthreads();        // da1 complete; the operand slabs are dead: they become the scratch of the conv-grad reduce
-  stamp(prof, 12, tid);
-  // ---- conv grads: each pooled cell routes da1 to its argmax conv position (3 groups of 256 threads, one per channel) ----
+  // ---- conv grads (under MMA 3): each pooled cell routes da1 to its argmax conv position; 3 groups of 256 threads, one
+  //      per channel; partial sums are folded over 4 neighbouring lanes and transposed through the dead W slabs -----------
   float cacc[26];
 #pragma unroll
   for (int i = 0; i < 26; ++i) cacc[i] = 0.f;
@@ -571,41 +578,47 @@ mnist_tc_train_kernel(const Args a, const __grid_constant__ CUtensorMap w1_map) 
       }
     }
   }
-  float* scratch = reinterpret_cast<float*>(sm.w_hi);   // [78][CGROUP] = 80 KB of the 96 KB of dead W / A slabs
-  if (cg < F) {
+  float* scratch = reinterpret_cast<float*>(sm.w_hi);   // [78][64]: 20 KB of the W slabs (dead since MMA 2 completed)
 #pragma unroll
-    for (int i = 0; i < 26; ++i) scratch[(cg * 26 + i) * CGROUP + ct] = cacc[i];
+  for (int i = 0; i < 26; ++i) {
+    float v = cacc[i];
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    if (cg < F && (lane & 3) == 0) scratch[(cg * 26 + i) * 64 + (ct >> 2)] = v;
   }
   __syncthreads();
   for (int o = warp; o < 78; o += NT / 32) {
-    float v = 0.f;
-#pragma unroll
-    for (int q = 0; q < CGROUP / 32; ++q) v += scratch[o * CGROUP + lane + 32 * q];
+    float v = scratch[o * 64 + lane] + scratch[o * 64 + lane + 32];
     v = warp_sum(v);
     if (lane == 0) {
       const int ch = o / 26, i = o - ch * 26;
-      sm.part[(i < 25) ? PART_WC + ch * 25 + i : PART_BC + ch] = v;
+      // this CTA's share of the conv gradients goes straight into rank 0's collection buffer
+      const int dst = (i < 25) ? ch * 25 + i : 75 + ch;
+      asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(map_to(sm.cpart + c * 80 + dst, 0u)), "f"(v) : "memory");
     }
   }
-  stamp(prof, 13, tid);
-  cluster_sync();                                        // #3: every CTA's share of the small gradients is in `part`
-  if (c == 0) {
-    for (int o = tid; o < PART_N; o += NT) {
-      float v = 0.f;
+  stamp(prof, 12, tid);
+  umma::mbar_wait(&sm.bar_m3, 0);
+  umma::fence_after_sync();
+  {
+    float v3[16];
+    umma::tmem_ld16(tmem + ((uint32_t)(32 * eq) << 16) + TM_D3 + 32 * ech + 16 * ehalf, v3);
+    if (lane < 16) {
+      float* gw = gp + a.off_w1 + erow * FC1_IN + ech * NPOOL + CELLS * c + 16 * ehalf;
 #pragma unroll
-      for (int r = 0; r < CL; ++r) v += ld_dsmem(map_to(sm.part + o, (uint32_t)r));
-      if (o < PART_BC) gp[a.off_wc + o] = v;
-      else if (o < PART_B1) gp[a.off_bc + (o - PART_BC)] = v;
-      else if (o < PART_W2) gp[a.off_b1 + (o - PART_B1)] = v;
-      else if (o < PART_B2) gp[a.off_w2 + (o - PART_W2)] = v;
-      else if (o < PART_LOSS) gp[a.off_b2 + (o - PART_B2)] = v;
-      else {
-        a.loss_part[l * nsplit + bsplit] = v;
-        if (a.loss_mirror != nullptr) a.loss_mirror[l * nsplit + bsplit] = v;     // zero-copy store to pinned host memory
-      }
+      for (int i = 0; i < 16; i += 4)
+        if (i < nvalid) *reinterpret_cast<float4*>(gw + i) = make_float4(v3[i], v3[i + 1], v3[i + 2], v3[i + 3]);
     }
   }
-  cluster_sync();                                        // #4: rank 0 is done reading the peers' shared memory
+  umma::fence_before_sync();
+  stamp(prof, 13, tid);
+  cluster_sync();                                        // #3: all six conv-gradient shares are in rank 0's buffer
+  if (c == 0 && tid < 78) {
+    float v = 0.f;
+#pragma unroll
+    for (int r = 0; r < CL; ++r) v += sm.cpart[r * 80 + tid];
+    gp[tid < 75 ? a.off_wc + tid : a.off_bc + (tid - 75)] = v;
+  }
   if (warp == 3) umma::tmem_dealloc(tmem, TM_COLS);
   stamp(prof, 14, tid);
 }

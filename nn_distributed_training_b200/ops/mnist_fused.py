@@ -103,7 +103,7 @@ class FusedMnist:
         if self.tc:
             self.base.update(tc=1, w1_map=self.ext.make_w1_tensor_map(a.theta.data_ptr(), a.n_pad, self.L, off[names[2]]))
         if os.environ.get("NNDT_STEP_PROF") == "1":     # scripts/profile_round_phases.py --per-step
-            self.step_prof = torch.zeros(self.L * self.S * (6 if self.tc else 1), 64, dtype=torch.int64, device=dev)
+            self.step_prof = torch.zeros(self.L * self.S * (6 if (self.tc or self.cl64) else 1), 64, dtype=torch.int64, device=dev)
             self.base["step_prof"] = self.step_prof.data_ptr()
         self.train_op = self.ext.MnistOp(self.base)
         self._setup_eval()

@@ -174,7 +174,7 @@ def test_consensus_kernels_fp64_with_autograd_model():
                  "metrics_config": {"evaluate_frequency": 100}, "optimizer_config": conf}
         torch.manual_seed(1)
         pr = DistMNISTProblem(nx.wheel_graph(N), MNISTConvNet(3, 5, 64, dtype=torch.float64), torch.nn.NLLLoss(),
-                              train, val, DEV, pconf)
+                              train, val, DEV, pconf, backend="torch")   # autograd model (float64 has fused kernels too now)
         assert pr.backend == "torch"
         DiNNO(pr, DEV, conf).train()
         outs.append(pr.arena.theta.clone())
