@@ -53,7 +53,7 @@ class FusedMnist:
         self.S = -(-self.B // self.spb)
         # paper shape, fp32, batch <= 64: the tcgen05 / TMEM K-split cluster kernel (csrc/mnist_tc.cu) — one gradient
         # row per node instead of S per-slice partials.  NNDT_MNIST_TC=0 keeps the batch-split mma.sync kernel (A/B).
-        self.tc = (not self.generic and self.B <= 64 and os.environ.get("NNDT_MNIST_TC", "0") != "0"
+        self.tc = (not self.generic and self.B <= 64 and os.environ.get("NNDT_MNIST_TC", "1") != "0"
                    and str(problem.conf.get("mnist_kernel", "tc")) == "tc" and self.ext.mnist_tc_max_clusters() >= 1)
         if self.tc:
             # batch splits per node (1, 2 or 4 clusters of 6 CTAs, M = 64 / 32 / 16 samples each): as many as keep all

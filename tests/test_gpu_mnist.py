@@ -386,7 +386,7 @@ def test_tc_kernel_matches_batch_split_kernel_and_autograd(B, float_inputs, monk
     old = _problem(3, B, "fused", conf, M=150, float_inputs=float_inputs)
     monkeypatch.delenv("NNDT_MNIST_TC")
     ref = _problem(3, B, "torch", conf, M=150, float_inputs=float_inputs)
-    assert tc.fused.tc and tc.fused.S == 1 and not old.fused.tc
+    assert tc.fused.tc and tc.fused.S in (1, 2, 4) and not old.fused.tc
     old.arena.theta.copy_(tc.arena.theta)
     ref.arena.theta.copy_(tc.arena.theta)
     for step in range(4):
