@@ -11,6 +11,8 @@
 // gradient row; small gradients are reduced by rank 0 through DSMEM.  One gradient partial row per cluster.
 // GEMM tiling: a thread owns 2 rows x 4-5 strided columns; with rows padded to 73 / 65 doubles every operand read is
 // either a broadcast or conflict free, so the loops run at the DFMA rate.
+#include <type_traits>
+
 #include "mnist_device.cuh"
 
 namespace nndt {
@@ -23,11 +25,11 @@ constexpr int PART_WC = 0, PART_BC = 75, PART_B1 = 78, PART_W2 = 142, PART_B2 = 
 
 struct Smem {
   double w[64 * WS];         // W1 slice [j][k], k = ch * 24 + cell; later da1 [s][72]
-  double a[64 * WS];         // A tile [s][k]
-  double dh[64 * HS];        // dH [s][j]
-  double hpart[64 * HS];     // partial H [s][j] (read by the peers)
-  float img[64 * 224];       // raw pixels of image rows 4c .. 4c+7 (u8 value or float value), [8][28] per sample
-  double h_loc[11 * 64];     // later the cross-warp scratch of the conv-grad reduction
+  double a[64 * WS];         // A tile [s][k]; later (with dh) the scratch of the conv-grad reduction
+  double dh[64 * HS];        // dH [s][j]; before that, split-K partial sums of GEMM 1
+  double hpart[64 * HS];     // partial H [s][j] (read by the peers); later split-K partial sums of GEMM 2
+  alignas(16) unsigned char img[64 * 224 * 4];   // image rows 4c .. 4c+7: MS <= 32: normalised doubles [MS][224]; MS = 64: raw floats
+  double h_loc[11 * 64];     // later (rank 0) the six CTAs' conv-gradient shares [6][80]
   double dh_loc[11 * 64];
   double part[800];
   double w2[NCLS * HID];
@@ -43,6 +45,7 @@ struct Smem {
   unsigned char arg[64 * KC];
 };
 static_assert(sizeof(Smem) <= 227 * 1024, "shared memory budget");
+static_assert(6 * 80 <= 11 * 64, "conv shares fit h_loc");
 
 NNDT_DEVINL void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -54,12 +57,17 @@ NNDT_DEVINL uint32_t map_to(const void* p, uint32_t rank) {
   return r;
 }
 NNDT_DEVINL double ld_dsmem(uint32_t a) { double v; asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory"); return v; }
+NNDT_DEVINL void st_dsmem(uint32_t a, double v) { asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
 NNDT_DEVINL double wsum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-
+NNDT_DEVINL double wmax(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
 NNDT_DEVINL void stamp(long long* prof, int idx, int tid) {
   if (prof != nullptr && tid == 0) {
     long long t;
@@ -80,6 +88,14 @@ mnist_cl64_train_kernel(const Args a, const GenericShape gs) {
   auto own_lo = [](int r) { return (MS * r + CL - 1) / CL; };
   const double pmean = gs.mean, pis = gs.inv_std;
   const bool u8 = a.x_is_u8 != 0;
+  // pixels: with MS <= 32 samples the 8 x 28 slabs fit as normalised doubles, so conv and conv-grad read fp64 directly
+  constexpr bool kDoublePix = MS <= 32;
+  using PT = typename std::conditional<kDoublePix, double, float>::type;
+  PT* img = reinterpret_cast<PT*>(sm.img);
+  auto pix = [&](PT v) -> double {
+    if constexpr (kDoublePix) return v;
+    else return u8 ? ((double)v * (1.0 / 255.0) - pmean) * pis : (double)v;
+  };
   long long* prof = a.prof != nullptr ? a.prof + ((l * nsplit + bsplit) * CL + c) * 64 : nullptr;
   stamp(prof, 0, tid);
 
@@ -122,16 +138,22 @@ mnist_cl64_train_kernel(const Args a, const GenericShape gs) {
       }
     }
   }
-
   stamp(prof, 1, tid);
   pdl_wait();                 // the parameters of this step are final
   pdl_launch_dependents();
   stamp(prof, 2, tid);
 
-  // ---- W1 slice [64 j][72 k] (three 24-column runs per row), small tensors, pixels ---------------------------------------
-  for (int o = tid; o < HID * KC; o += NT) {
-    const int j = o / KC, r = o - j * KC, ch = r / CELLS, cell = r - ch * CELLS;
-    sm.w[j * WS + r] = __ldcg(th + a.off_w1 + (size_t)j * FC1_IN + ch * NPOOL + CELLS * c + cell);
+  // ---- W1 slice [64 j][72 k] (three 24-column runs per row): loads in flight while the pixels are converted --------------
+  constexpr int NW = (HID * KC + NT - 1) / NT;
+  double wreg[NW];
+#pragma unroll
+  for (int i = 0; i < NW; ++i) {
+    const int o = tid + i * NT;
+    wreg[i] = 0.0;
+    if (o < HID * KC) {
+      const int j = o / KC, r = o - j * KC, ch = r / CELLS, cell = r - ch * CELLS;
+      wreg[i] = __ldcg(th + a.off_w1 + (size_t)j * FC1_IN + ch * NPOOL + CELLS * c + cell);
+    }
   }
   for (int o = tid; o < NCLS * HID; o += NT) sm.w2[o] = __ldcg(th + a.off_w2 + o);
   if (tid < 75) sm.wc[tid] = __ldcg(th + a.off_wc + tid);
@@ -145,34 +167,42 @@ mnist_cl64_train_kernel(const Args a, const GenericShape gs) {
       if (o < MS * 14) {
         const int s = o / 14, q = o - s * 14;
         const uint32_t w[4] = {pu[i].x, pu[i].y, pu[i].z, pu[i].w};
-        float* dst = sm.img + s * 224 + 16 * q;
+        PT* dst = img + s * 224 + 16 * q;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) dst[j] = (float)((w[j >> 2] >> (8 * (j & 3))) & 0xff);
+        for (int j = 0; j < 16; ++j) {
+          const double v = (double)((w[j >> 2] >> (8 * (j & 3))) & 0xff);
+          if constexpr (kDoublePix) dst[j] = (v * (1.0 / 255.0) - pmean) * pis; else dst[j] = (float)v;
+        }
       }
     }
   } else {
 #pragma unroll
     for (int i = 0; i < NF4; ++i) {
       const int o = tid + i * NT;
-      if (o < MS * 56) *reinterpret_cast<float4*>(sm.img + (o / 56) * 224 + 4 * (o % 56)) = pf[i];
+      if (o < MS * 56) {
+        PT* dst = img + (o / 56) * 224 + 4 * (o % 56);
+        dst[0] = (PT)pf[i].x; dst[1] = (PT)pf[i].y; dst[2] = (PT)pf[i].z; dst[3] = (PT)pf[i].w;
+      }
     }
+  }
+#pragma unroll
+  for (int i = 0; i < NW; ++i) {
+    const int o = tid + i * NT;
+    if (o < HID * KC) sm.w[(o / KC) * WS + (o % KC)] = wreg[i];
   }
   __syncthreads();
   stamp(prof, 3, tid);
 
-  // ---- conv + ReLU + maxpool: one (sample, pooled cell) per item, the 6x6 patch normalised to fp64 once -----------------
+  // ---- conv + ReLU + maxpool: one (sample, pooled cell) per item, the 6x6 patch in fp64 registers ---------------------------
   for (int it = tid; it < MS * CELLS; it += NT) {
     const int s = it / CELLS, cell = it - s * CELLS;
     const int pr = cell / PHW, px = cell - pr * PHW;
-    const float* src = sm.img + s * 224 + (2 * pr) * HW + 2 * px;
+    const PT* src = img + s * 224 + (2 * pr) * HW + 2 * px;
     double patch[6][6];
 #pragma unroll
     for (int r = 0; r < 6; ++r)
 #pragma unroll
-      for (int q = 0; q < 6; ++q) {
-        const double v = (double)src[r * HW + q];
-        patch[r][q] = u8 ? (v * (1.0 / 255.0) - pmean) * pis : v;
-      }
+      for (int q = 0; q < 6; ++q) patch[r][q] = pix(src[r * HW + q]);
     const bool ok = sm.valid[s] != 0.f;
 #pragma unroll 1
     for (int ch = 0; ch < F; ++ch) {
@@ -196,21 +226,23 @@ mnist_cl64_train_kernel(const Args a, const GenericShape gs) {
     }
   }
   __syncthreads();
-
   stamp(prof, 4, tid);
+
   // ---- GEMM 1: H_c[s][j] = sum_k A[s][k] W[j][k].  Register tile 4 rows x 4 columns (rows tr + RQ i, columns tc + 16 i):
-  //      per k a warp issues 4 + 4 shared-memory wavefronts for 16 DFMA instructions, which balances the 128 B/clk of shared
-  //      memory against the 64 DFMA/clk of the SM; MS * 4 threads are busy.
-  constexpr int RQ = MS / 4;                              // row-group count; thread t < MS * 4
-  const int tr = tid >> 4, tc = tid & 15;
-  if (tid < MS * 4) {
+  //      per k a warp issues 4 + 4 shared-memory wavefronts for 16 DFMA instructions.  Split-K over NG = 512 / (4 MS) thread
+  //      groups; group g writes its partial tile to P_g (the contiguous dh + hpart arrays hold NG x MS = 128 rows) and the
+  //      partials are summed in fixed order (deterministic) into the rows the peers read.
+  constexpr int RQ = MS / 4, GT = MS * 4, NG = NT / GT, KG = KC / NG;
+  static_assert(KC % NG == 0 && NG * MS == 128, "split-K geometry");
+  const int grp = tid / GT, tg = tid - grp * GT, tr = tg >> 4, tc = tg & 15;
+  {
     double acc[4][4];
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[r][i] = 0.0;
 #pragma unroll 2
-    for (int k = 0; k < KC; ++k) {
+    for (int k = grp * KG; k < (grp + 1) * KG; ++k) {
       double x[4], wv[4];
 #pragma unroll
       for (int r = 0; r < 4; ++r) x[r] = sm.a[(tr + RQ * r) * WS + k];
@@ -221,10 +253,19 @@ mnist_cl64_train_kernel(const Args a, const GenericShape gs) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[r][i] += x[r] * wv[i];
     }
+    double* P = sm.dh + (size_t)grp * MS * HS;
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) sm.hpart[(tr + RQ * r) * HS + tc + 16 * i] = acc[r][i];
+      for (int i = 0; i < 4; ++i) P[(tr + RQ * r) * HS + tc + 16 * i] = acc[r][i];
+  }
+  __syncthreads();
+  for (int o = tid; o < MS * HID; o += NT) {
+    const int s = o >> 6, j = o & 63;
+    double v = 0.0;
+#pragma unroll
+    for (int g = 0; g < NG; ++g) v += sm.dh[(size_t)g * MS * HS + s * HS + j];
+    sm.hpart[s * HS + j] = v;                         // hpart == P_{64 / MS}: every element is read before it is rewritten
   }
   stamp(prof, 5, tid);
   cluster_sync();                                        // #1: all six partial H are in shared memory
@@ -260,21 +301,17 @@ mnist_cl64_train_kernel(const Args a, const GenericShape gs) {
     if (live && part == 0) sm.z[sl * 16 + cc] = v + sm.b2[cc];
   }
   __syncthreads();
-  if (tid < ns) {
-    const int sl = tid, s = s0 + sl;
-    double mx = sm.z[sl * 16];
-#pragma unroll
-    for (int cc = 1; cc < NCLS; ++cc) mx = fmax(mx, sm.z[sl * 16 + cc]);
-    double se = 0.0;
-#pragma unroll
-    for (int cc = 0; cc < NCLS; ++cc) se += exp(sm.z[sl * 16 + cc] - mx);
+  if (warp < ns) {                                       // log-softmax + NLL: one warp per sample, one lane per class
+    const int sl = warp, s = s0 + sl;
+    const bool cls = lane < NCLS;
+    const double zc = cls ? sm.z[sl * 16 + lane] : -1.0e300;
+    const double mx = wmax(zc);
+    const double se = wsum(cls ? exp(zc - mx) : 0.0);
     const double lse = mx + log(se);
     const int y = sm.label[s];
     const double ok = (double)sm.valid[s];
-#pragma unroll
-    for (int cc = 0; cc < NCLS; ++cc)
-      sm.dz[sl * 16 + cc] = ok * inv_bs * (exp(sm.z[sl * 16 + cc] - lse) - (cc == y ? 1.0 : 0.0));
-    sm.red[sl] = ok * (lse - sm.z[sl * 16 + y]);
+    if (cls) sm.dz[sl * 16 + lane] = ok * inv_bs * (exp(zc - lse) - (lane == y ? 1.0 : 0.0));
+    if (lane == y) sm.red[sl] = ok * (lse - zc);
   }
   __syncthreads();
   for (int o = tid; o < ns * HID; o += NT) {
@@ -305,9 +342,26 @@ mnist_cl64_train_kernel(const Args a, const GenericShape gs) {
     sm.part[PART_LOSS] = v * inv_bs;
   }
   stamp(prof, 7, tid);
-  cluster_sync();                                        // #2: every owner's dH rows are final
+  cluster_sync();                                        // #2: every owner's dH rows and fc2 / b1 / loss shares are final
   stamp(prof, 8, tid);
-
+  double* gp = reinterpret_cast<double*>(a.grad_part) + ((size_t)l * nsplit + bsplit) * a.n_pad;
+  // CTA c reduces its sixth of the fc2 / b1 / loss shares over the cluster (the peers stay resident until the last barrier)
+  {
+    constexpr int NE = PART_N - PART_B1, PER = (NE + CL - 1) / CL;
+    const int o = PART_B1 + c * PER + tid;
+    if (tid < PER && o < PART_N) {
+      double v = 0.0;
+#pragma unroll
+      for (int r = 0; r < CL; ++r) v += ld_dsmem(map_to(sm.part + o, (uint32_t)r));
+      if (o < PART_W2) gp[a.off_b1 + (o - PART_B1)] = v;
+      else if (o < PART_B2) gp[a.off_w2 + (o - PART_W2)] = v;
+      else if (o < PART_LOSS) gp[a.off_b2 + (o - PART_B2)] = v;
+      else {
+        a.loss_part[l * nsplit + bsplit] = (float)v;
+        if (a.loss_mirror != nullptr) a.loss_mirror[l * nsplit + bsplit] = (float)v;
+      }
+    }
+  }
   // ---- gather all MS dH rows from their owners ------------------------------------------------------------------------------
   for (int o = tid; o < MS * HID; o += NT) {
     const int s = o >> 6, j = o & 63;
@@ -317,17 +371,19 @@ mnist_cl64_train_kernel(const Args a, const GenericShape gs) {
     sm.dh[s * HS + j] = ld_dsmem(map_to(sm.dh_loc + (s - own_lo(r)) * HID + j, (uint32_t)r));
   }
   __syncthreads();
-
   stamp(prof, 9, tid);
-  // ---- GEMM 2: da1_c[s][k] = sum_j dH[s][j] W[j][k]; tile 4 rows x 5 columns (k = tc + 16 i < 72) -------------------------
+
+  // ---- GEMM 2: da1_c[s][k] = sum_j dH[s][j] W[j][k]; tile 4 rows x 5 columns (k = tc + 16 i < 72).  With MS <= 32 the j range
+  //      is split over two thread groups: group 1 parks its partial tile in the (dead) hpart rows, group 0 adds it -----------
+  constexpr int NG2 = (MS <= 32) ? 2 : 1, JG = HID / NG2;
   double d2[4][5];
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int i = 0; i < 5; ++i) d2[r][i] = 0.0;
-  if (tid < MS * 4) {
+  if (grp < NG2) {
 #pragma unroll 2
-    for (int j = 0; j < HID; ++j) {
+    for (int j = grp * JG; j < (grp + 1) * JG; ++j) {
       double x[4], wv[5];
 #pragma unroll
       for (int r = 0; r < 4; ++r) x[r] = sm.dh[(tr + RQ * r) * HS + j];
@@ -338,11 +394,18 @@ mnist_cl64_train_kernel(const Args a, const GenericShape gs) {
 #pragma unroll
         for (int i = 0; i < 5; ++i) d2[r][i] += x[r] * wv[i];
     }
+    if (NG2 == 2 && grp == 1) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+          if (tc + 16 * i < KC) sm.hpart[(tr + RQ * r) * KC + tc + 16 * i] = d2[r][i];
+    }
   }
   stamp(prof, 10, tid);
-  // ---- GEMM 3: dW1_c[j][k] = sum_s dH[s][j] A[s][k]; tile 4 features (tr + 16 r, tr < 16) x 5 columns; 256 threads --------
-  double* gp = reinterpret_cast<double*>(a.grad_part) + ((size_t)l * nsplit + bsplit) * a.n_pad;
+  // ---- GEMM 3: dW1_c[j][k] = sum_s dH[s][j] A[s][k]; tile 4 features (tr3 + 16 r) x 5 columns; 256 threads -----------------
   if (tid < 256) {
+    const int tr3 = tid >> 4, tc3 = tid & 15;
     double d3[4][5];
 #pragma unroll
     for (int r = 0; r < 4; ++r)
@@ -352,9 +415,9 @@ mnist_cl64_train_kernel(const Args a, const GenericShape gs) {
     for (int s = 0; s < MS; ++s) {
       double x[4], av[5];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) x[r] = sm.dh[s * HS + tr + 16 * r];
+      for (int r = 0; r < 4; ++r) x[r] = sm.dh[s * HS + tr3 + 16 * r];
 #pragma unroll
-      for (int i = 0; i < 5; ++i) av[i] = (tc + 16 * i < KC) ? sm.a[s * WS + tc + 16 * i] : 0.0;
+      for (int i = 0; i < 5; ++i) av[i] = (tc3 + 16 * i < KC) ? sm.a[s * WS + tc3 + 16 * i] : 0.0;
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -362,25 +425,28 @@ mnist_cl64_train_kernel(const Args a, const GenericShape gs) {
     }
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
-      const int k = tc + 16 * i;
+      const int k = tc3 + 16 * i;
       if (k < KC) {
         const int ch = k / CELLS, cell = k - ch * CELLS;
         double* g = gp + a.off_w1 + ch * NPOOL + CELLS * c + cell;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) g[(size_t)(tr + 16 * r) * FC1_IN] = d3[r][i];
+        for (int r = 0; r < 4; ++r) g[(size_t)(tr3 + 16 * r) * FC1_IN] = d3[r][i];
       }
     }
   }
-  __syncthreads();      // every read of W (GEMM 2) and of A / dH (GEMM 3) is done
+  __syncthreads();      // every read of W (GEMM 2) and of A / dH (GEMM 3) is done; group 1's partial tile is parked
   stamp(prof, 11, tid);
   double* da1 = sm.w;   // W's rows become da1 [s][72], masked by ReLU'(a1)
-  if (tid < MS * 4) {
+  if (grp == 0) {
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
         const int s = tr + RQ * r, k = tc + 16 * i;
-        if (k < KC) da1[s * KC + k] = (sm.arg[s * KC + k] & 4) ? d2[r][i] : 0.0;
+        if (k < KC) {
+          const double v = d2[r][i] + (NG2 == 2 ? sm.hpart[s * KC + k] : 0.0);
+          da1[s * KC + k] = (sm.arg[s * KC + k] & 4) ? v : 0.0;
+        }
       }
   }
   __syncthreads();
@@ -399,14 +465,11 @@ mnist_cl64_train_kernel(const Args a, const GenericShape gs) {
       if (g != 0.0) {
         const int ai = sm.arg[s * KC + ch * CELLS + cell] & 3;
         const int pr = cell / PHW, px = cell - pr * PHW;
-        const float* src = sm.img + s * 224 + (2 * pr + (ai >> 1)) * HW + 2 * px + (ai & 1);
+        const PT* src = img + s * 224 + (2 * pr + (ai >> 1)) * HW + 2 * px + (ai & 1);
 #pragma unroll
         for (int ky = 0; ky < KS; ++ky)
 #pragma unroll
-          for (int kx = 0; kx < KS; ++kx) {
-            const double v = (double)src[ky * HW + kx];
-            cacc[ky * 5 + kx] += g * (u8 ? (v * (1.0 / 255.0) - pmean) * pis : v);
-          }
+          for (int kx = 0; kx < KS; ++kx) cacc[ky * 5 + kx] += g * pix(src[ky * HW + kx]);
         cacc[25] += g;
       }
     }
@@ -421,29 +484,19 @@ mnist_cl64_train_kernel(const Args a, const GenericShape gs) {
 #pragma unroll
       for (int q = 0; q < NT / 64; ++q) v += scratch[o * (NT / 2) + lane + 32 * q];
       v = wsum(v);
-      if (lane == 0) sm.part[o < 25 ? PART_WC + ch * 25 + o : PART_BC + ch] = v;
+      // this CTA's share goes straight into rank 0's collection buffer (its h_loc rows, dead since barrier #2)
+      if (lane == 0) st_dsmem(map_to(sm.h_loc + c * 80 + (o < 25 ? ch * 25 + o : 75 + ch), 0u), v);
     }
     __syncthreads();
   }
   stamp(prof, 12, tid);
-  cluster_sync();                                        // #3: every CTA's share of the small gradients is in `part`
-  if (c == 0) {
-    for (int o = tid; o < PART_N; o += NT) {
-      double v = 0.0;
+  cluster_sync();                                        // #3: all six conv-gradient shares are in rank 0's buffer
+  if (c == 0 && tid < 78) {
+    double v = 0.0;
 #pragma unroll
-      for (int r = 0; r < CL; ++r) v += ld_dsmem(map_to(sm.part + o, (uint32_t)r));
-      if (o < PART_BC) gp[a.off_wc + o] = v;
-      else if (o < PART_B1) gp[a.off_bc + (o - PART_BC)] = v;
-      else if (o < PART_W2) gp[a.off_b1 + (o - PART_B1)] = v;
-      else if (o < PART_B2) gp[a.off_w2 + (o - PART_W2)] = v;
-      else if (o < PART_LOSS) gp[a.off_b2 + (o - PART_B2)] = v;
-      else {
-        a.loss_part[l * nsplit + bsplit] = (float)v;
-        if (a.loss_mirror != nullptr) a.loss_mirror[l * nsplit + bsplit] = (float)v;
-      }
-    }
+    for (int r = 0; r < CL; ++r) v += sm.h_loc[r * 80 + tid];
+    gp[tid < 75 ? a.off_wc + tid : a.off_bc + (tid - 75)] = v;
   }
-  cluster_sync();                                        // #4: rank 0 is done reading the peers' shared memory
   stamp(prof, 13, tid);
 }
 
