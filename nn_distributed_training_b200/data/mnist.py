@@ -53,7 +53,8 @@ def synthetic_mnist(num: int, seed: int = 0, noise: float = 0.35, classes=None) 
     return Shard(x, labels, (MNIST_MEAN, MNIST_STD))
 
 
-def synthetic_mnist_hard(num: int, seed: int = 0, label_noise: float = 0.02) -> Shard:
+def synthetic_mnist_hard(num: int, seed: int = 0, label_noise: float = 0.02, dropout: float = 0.25, shift: int = 3,
+                         noise: float = 0.55) -> Shard:
     """A NON-separable 10-class stand-in for MNIST (on ``synthetic_mnist`` every algorithm reaches
     100 %, so accuracy-vs-rounds cannot tell DSGD from DiNNO).  Classes are built from a shared pool of strokes — every
     class shares three of its five strokes with other classes — each sample drops strokes at random, is translated by up
@@ -81,14 +82,14 @@ def synthetic_mnist_hard(num: int, seed: int = 0, label_noise: float = 0.02) -> 
     for a in range(0, num, chunk):
         sl = slice(a, min(num, a + chunk))
         n = sl.stop - sl.start
-        keep = rng.random((n, 5)) > 0.25                               # stroke dropout
+        keep = rng.random((n, 5)) > dropout                            # stroke dropout
         keep[np.arange(n), rng.integers(0, 5, n)] = True               # at least one stroke survives
         w = keep * rng.uniform(0.6, 1.0, (n, 5))
         blk = np.einsum("nk,nkhw->nhw", w.astype(np.float32), pn[members[labels[sl]]])
-        sh = rng.integers(-3, 4, (n, 2))
+        sh = rng.integers(-shift, shift + 1, (n, 2))
         for i in range(n):
             blk[i] = np.roll(blk[i], (sh[i, 0], sh[i, 1]), (0, 1))
-        blk += 0.55 * rng.random(blk.shape, dtype=np.float32)
+        blk += noise * rng.random(blk.shape, dtype=np.float32)
         np.clip(blk, 0.0, 1.0, out=blk)
         out[sl] = (blk * 255.0).astype(np.uint8)
     flip = rng.random(num) < label_noise

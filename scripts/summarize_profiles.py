@@ -73,6 +73,12 @@ def launches(name):
 
 if __name__ == "__main__":
     launches("launches_mnist")
+    launches("launches_tc")
+    launches("launches_f64")
+    summarize("mnist_tc", "mnist_tc_train_kernel<32> — tcgen05 / TMEM / TMA conv-net forward+backward, 10 nodes x 2 clusters x 6 CTAs (120 CTAs)",
+              "Algorithmic bytes per launch: parameters 10 x 111 KB (W1 slices are TMA-loaded exactly once per cluster: 2 x 111 KB per node), one "
+              "640 x 784 B batch, gradient rows 20 x 111 KB written once.")
+    summarize("mnist_cl64", "mnist_cl64_train_kernel<32> — float64 K-split cluster conv-net forward+backward (fp64 CUDA cores), 120 CTAs", "")
     summarize("mnist_train", "mnist_kernel<5,768,train> — fused MNIST conv-net forward+backward, 10 nodes x 13 batch slices (130 CTAs)", "")
     summarize("mnist_eval", "mnist_kernel<8,768,eval> — forward-only validation pass", "")
     summarize("dinno_update", "dinno_update_kernel<float> — fused neighbor pull + dual ascent + prox-gradient + Adam", "")
