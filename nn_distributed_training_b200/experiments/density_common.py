@@ -86,4 +86,5 @@ def train_solo(model, loss, train_set, val_set, device, conf):
             vloss += loss(torch.squeeze(model(va.x[a: a + vb].to(dtype))), va.y[a: a + vb].to(dtype))
         mesh = mesh_inputs(val_set, device, dtype)
         dense = model(mesh)
-    return {"validation_loss": vloss, "mesh_grid_density": dense, "mesh_grid": mesh}
+    # CPU tensors: solo_results.pt must load on a machine without a GPU (the notebooks / visualization tools)
+    return {"validation_loss": vloss.cpu(), "mesh_grid_density": dense.cpu(), "mesh_grid": mesh.cpu()}
