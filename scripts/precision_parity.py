@@ -28,6 +28,10 @@ from nn_distributed_training_b200.optimizers import build_optimizer  # noqa: E40
 from nn_distributed_training_b200.problems.dist_mnist_problem import DistMNISTProblem  # noqa: E402
 
 N = 10
+# difficulty presets of data/mnist.py: synthetic_mnist_hard
+PRESETS = {"hard": dict(),                                                        # + 2 % label noise
+           "hard_clean": dict(label_noise=0.0, dropout=0.25, shift=3, noise=0.55),   # same images, clean labels
+           "medium": dict(label_noise=0.0, dropout=0.1, shift=2, noise=0.45)}
 METRICS = ["forward_pass_count", "validation_loss", "consensus_error", "top1_accuracy", "current_epoch"]
 
 
@@ -112,12 +116,15 @@ def main():
     ap.add_argument("--algs", default="dinno,dsgt,dsgd")
     ap.add_argument("--ref-algs", default="dinno")
     ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "precision_parity.md"))
+    ap.add_argument("--preset", default="hard", choices=sorted(PRESETS))
     args = ap.parse_args()
-    train, val = synthetic_mnist_hard(60000, seed=0), synthetic_mnist_hard(10000, seed=1)
+    kw = PRESETS[args.preset]
+    train, val = synthetic_mnist_hard(60000, seed=0, **kw), synthetic_mnist_hard(10000, seed=1, **kw)
     sh = shards(train)
     lines = ["# Precision parity: fp32 fused vs fp64 fused vs the fp64 reference", "",
              f"dist_mnist_PAPER hyper-parameters, N = {N} cycle, hetero split (one class per node), batch 64, {args.rounds} rounds, "
-             "`synthetic_mnist_hard` (non-separable: shared strokes, stroke dropout, +-3 px shifts, heavy noise, 2 % label noise).",
+             f"`synthetic_mnist_hard` preset `{args.preset}` {PRESETS[args.preset] or '(defaults: stroke dropout 0.25, +-3 px shifts, noise 0.55, 2 % label noise)'} "
+             "(classes share strokes; samples drop strokes at random, are shifted and buried in noise).",
              "Same shards, same initial weights; ours fp32 / fp64 also share the minibatch sequence (stateless sampler), the reference "
              "draws its own DataLoader order.  `traj` = ||theta_fp32 - theta_fp64|| / ||theta_fp64|| over all nodes.", ""]
     results = {}
