@@ -284,7 +284,7 @@ def measure_headline(h, ctx, args, dtype, sampler=None, probe=False):
     out = {"ms_per_step": ms / K, "value": n_nodes * K / (ms / 1e3), "launches": K * prog.launches_per_round(),
            "pipeline": prog.pipeline, "symm": prog.eng.pub_buf.how, "flags": prog.eng.flag_mode,
            "fwd_bwd_kernel": ("convnet_generic_kernel<%s> (CUDA cores)" % ("double" if dtype == "fp64" else "float"))
-           if pr.fused.generic else getattr(pr.fused, "kernel_name", "mnist_kernel (3xTF32 mma)")}
+           if (pr.fused.generic and not pr.fused.cl64) else pr.fused.kernel_name}
     if probe:   # per-call fixed cost: t(K) = intercept + slope K  (K = 20 is the production chunk, evaluate_frequency 20)
         pts = []
         for kk in (4, 20, 64, 256):

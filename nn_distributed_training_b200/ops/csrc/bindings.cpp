@@ -108,6 +108,7 @@ static consensus::Common<T> common_from(const py::dict& d) {
   c.flag_pull = geti(d, "flag_pull", 0); c.peer_pub = ptr<const int64_t>(d, "peer_pub");
   c.notify_mask = d.contains("notify_mask") ? d["notify_mask"].cast<unsigned long long>() : ~0ull;
   c.node_order = ptr<const int>(d, "node_order");
+  c.timeline = ptr<long long>(d, "timeline");
   c.pub_seq = ptr<int>(d, "pub_seq"); c.nbr_seq = ptr<const int64_t>(d, "nbr_seq");
   c.sum_mode = geti(d, "sum_mode", 0); c.n_total = geti(d, "n_total", 0);
   c.sum_local = ptr<double>(d, "sum_local"); c.sum_mc = ptr<const double>(d, "sum_mc");

@@ -81,7 +81,9 @@ __global__ void __launch_bounds__(THREADS) dinno_update_kernel(const DinnoArgs<T
   const DinnoCoef<T> cf = dinno_coef(a, ri.k, a.step, deg);
   const T rho = cf.rho;
   const bool first = a.step == 0, last = a.step == a.pits - 1;
+  tl_stamp(c, ri.k, a.step, 0);
   if (first) { if (c.sum_mode) wait_all_sums(c, ri.k); else wait_neighbors(c, ri.gid, l, ri.k); }
+  tl_stamp(c, ri.k, a.step, 1);
 
   const bool fresh = first && !a.persistent;  // Adam moments restart every round (reference Q3)
 
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(THREADS) dinno_update_kernel(const DinnoArgs<T
         v = ldv(a.v + row + i);
       }
     }
-    if (!waited) { pdl_wait(); pdl_launch_dependents(); waited = true; }
+    if (!waited) { tl_stamp(c, ri.k, a.step, 2); pdl_wait(); pdl_launch_dependents(); waited = true; tl_stamp(c, ri.k, a.step, 3); }
     const Pack<T> gl = sum_partials(c, l, i);
     dinno_apply(cf, th, thk, dl, du, m, v, gl);
     if (a.opt != kSGD) {
@@ -148,6 +150,7 @@ __global__ void __launch_bounds__(THREADS) dinno_update_kernel(const DinnoArgs<T
     if (last) stv(pub_row(c, ri.par ^ 1, 0, l) + i, th);
   }
   if (!waited) { pdl_wait(); pdl_launch_dependents(); }
+  tl_stamp(c, ri.k, a.step, 4);
   step_bookkeeping(c, l);
   if (last) { tag_published(c, l, ri.k); finish_round(c, ri.k); }
 }

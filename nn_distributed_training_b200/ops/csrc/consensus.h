@@ -52,6 +52,7 @@ struct Common {
   const int64_t* peer_pub;    // [world] address of rank r's own counter (pull mode)
   unsigned long long notify_mask;  // ranks that ever own a neighbor of a local node: the only ones told about a new round
   const int* node_order;      // [L] launch order of the local nodes (nodes with remote neighbors first), nullptr = identity
+  long long* timeline;        // debug (NNDT_TIMELINE=1): [4096][16] %globaltimer stamps of the update kernels, nullptr = off
   unsigned int* done_ctr;     // [1] last-block detection
   int* err;                   // [1] 1 = spin timeout, 2 = sequence check failed
   // optional debug build of the protocol: every published row carries the round it belongs to and every

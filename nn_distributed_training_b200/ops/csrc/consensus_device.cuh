@@ -46,6 +46,17 @@ NNDT_DEVINL int node_of_block(const Common<T>& c) {
   return c.node_order != nullptr ? c.node_order[blockIdx.y] : (int)blockIdx.y;
 }
 
+// debug timeline: stamp `which` (0..7) of update launch (round k, primal step) by the first and the last block of the grid
+template <typename T>
+NNDT_DEVINL void tl_stamp(const Common<T>& c, int k, int step, int which) {
+  if (c.timeline == nullptr || threadIdx.x != 0) return;
+  const bool first = blockIdx.x == 0 && blockIdx.y == 0, last = blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1;
+  if (!first && !last) return;
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  c.timeline[(size_t)((k * 4 + step) & 4095) * 16 + (first ? 0 : 8) + which] = t;
+}
+
 // spin until rank r has published round k (push: peers store into our local slot; pull: poll r's own counter over NVLink)
 template <typename T>
 NNDT_DEVINL void wait_rank(const Common<T>& c, int r, int k) {

@@ -187,6 +187,10 @@ class ConsensusEngine:
                  flag_pull=int(self.flag_mode == "pull"), peer_pub=self.t_peer_pub.data_ptr(),
                  notify_mask=int(self.notify_mask) if ctx.world_size > 1 else 0,
                  node_order=self.t_node_order.data_ptr() if ctx.world_size > 1 else None)
+        self.timeline = None
+        if os.environ.get("NNDT_TIMELINE") == "1":       # debug: %globaltimer stamps of the update kernels (scripts/timeline_rounds.py)
+            self.timeline = torch.zeros(4096, 16, dtype=torch.int64, device=dev)
+            d["timeline"] = self.timeline.data_ptr()
         # the C++ side indexes pub rows with stride L; when ranks host different node counts the
         # published buffer is allocated with the max count, so pass that as the row count of pub
         d["L"] = L
