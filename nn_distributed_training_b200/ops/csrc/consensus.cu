@@ -16,6 +16,9 @@
 // (st.release.sys over NVLink after __threadfence_system()); consumers spin with
 // ld.acquire.sys on their *local* flag array only for the ranks that own a neighbor.  Since a
 // node publishes k+1 only after finishing its round-k reads, two buffers suffice.
+#include <mutex>
+#include <unordered_map>
+
 #include "consensus_device.cuh"
 
 namespace nndt {
@@ -71,7 +74,7 @@ __global__ void publish_round_kernel(const Common<T> c) {
 }
 
 // ------------------------------------------------------------------ DiNNO ----
-template <typename T>
+template <typename T, int U>
 __global__ void __launch_bounds__(THREADS) dinno_update_kernel(const DinnoArgs<T> a) {
   const Common<T>& c = a.c;
   constexpr int N = Vec<T>::N;
@@ -140,7 +143,7 @@ __global__ void __launch_bounds__(THREADS) dinno_update_kernel(const DinnoArgs<T
       }
     }
     if (!waited) { tl_stamp(c, ri.k, a.step, 2); pdl_wait(); pdl_launch_dependents(); waited = true; tl_stamp(c, ri.k, a.step, 3); }
-    const Pack<T> gl = sum_partials(c, l, i);
+    const Pack<T> gl = sum_partials<U>(c, l, i);
     dinno_apply(cf, th, thk, dl, du, m, v, gl);
     if (a.opt != kSGD) {
       stv(a.m + row + i, m);
@@ -197,7 +200,7 @@ __global__ void __launch_bounds__(THREADS) dsgd_mix_kernel(const Common<T> c) {
   }
 }
 
-template <typename T>
+template <typename T, int U>
 __global__ void __launch_bounds__(THREADS) dsgd_step_kernel(const Common<T> c) {
   pdl_wait();
   pdl_launch_dependents();
@@ -208,7 +211,7 @@ __global__ void __launch_bounds__(THREADS) dsgd_step_kernel(const Common<T> c) {
   const size_t row = (size_t)l * c.n_pad;
   for (int i = (blockIdx.x * THREADS + threadIdx.x) * N; i < c.n_pad; i += gridDim.x * THREADS * N) {
     Pack<T> th = ldv(c.theta + row + i);
-    const Pack<T> g = sum_partials(c, l, i);
+    const Pack<T> g = sum_partials<U>(c, l, i);
 #pragma unroll
     for (int u = 0; u < N; ++u) th.v[u] -= alpha * g.v[u];
     stv(c.theta + row + i, th);
@@ -221,7 +224,7 @@ __global__ void __launch_bounds__(THREADS) dsgd_step_kernel(const Common<T> c) {
 
 // ------------------------------------------------------------------- DSGT ----
 // channel 0 of the published buffer is theta, channel 1 the gradient tracker y.
-template <typename T>
+template <typename T, int U>
 __global__ void __launch_bounds__(THREADS) dsgt_init_kernel(const DsgtArgs<T> a) {
   pdl_wait();
   pdl_launch_dependents();
@@ -230,7 +233,7 @@ __global__ void __launch_bounds__(THREADS) dsgt_init_kernel(const DsgtArgs<T> a)
   const int l = node_of_block(c);
   const size_t row = (size_t)l * c.n_pad;
   for (int i = (blockIdx.x * THREADS + threadIdx.x) * N; i < c.n_pad; i += gridDim.x * THREADS * N) {
-    const Pack<T> g = sum_partials(c, l, i);
+    const Pack<T> g = sum_partials<U>(c, l, i);
     stv(a.g_old + row + i, g);
     stv(pub_row(c, 0, 1, l) + i, g);
   }
@@ -285,7 +288,7 @@ __global__ void __launch_bounds__(THREADS) dsgt_mix_kernel(const DsgtArgs<T> a) 
   }
 }
 
-template <typename T>
+template <typename T, int U>
 __global__ void __launch_bounds__(THREADS) dsgt_track_kernel(const DsgtArgs<T> a) {
   pdl_wait();
   pdl_launch_dependents();
@@ -322,7 +325,7 @@ __global__ void __launch_bounds__(THREADS) dsgt_track_kernel(const DsgtArgs<T> a
           }
       }
     }
-    const Pack<T> gn = sum_partials(c, l, i);
+    const Pack<T> gn = sum_partials<U>(c, l, i);
     const Pack<T> go = ldv(a.g_old + row + i);
 #pragma unroll
     for (int u = 0; u < N; ++u) y.v[u] += gn.v[u] - go.v[u];
@@ -425,11 +428,33 @@ cudaError_t launch_spin(long long cycles, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------- launchers ----
-template <typename T>
-static dim3 grid_for(const Common<T>& c) {
+// One wave: the grid of an update kernel is capped at the number of CTAs that can be resident at once (the kernels
+// loop over the row with a grid stride).  A second wave costs a full CTA start-up + the dependent header loads
+// (round counter -> schedules -> topology -> data, ~4 L2 round trips), more than a second loop iteration does.
+template <typename K>
+static int resident_ctas(K kernel) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, int> cache;       // per kernel instantiation (one device type per process)
+  std::lock_guard<std::mutex> lock(mu);
+  const void* key = reinterpret_cast<const void*>(kernel);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  int dev = 0, sms = 0, occ = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, THREADS, 0) != cudaSuccess || occ < 1) occ = 1;
+  return cache[key] = sms * occ;
+}
+template <typename T, typename K>
+static dim3 grid_for(const Common<T>& c, K kernel) {
   const int per_block = THREADS * Vec<T>::N;
   int gx = (c.n_pad + per_block - 1) / per_block;
-  return dim3(gx, c.L);
+  const int slots = resident_ctas(kernel);
+  if (gx * c.L > slots) {
+    const int iters = (gx * c.L + slots - 1) / slots;       // loop iterations per thread that make it fit
+    gx = (gx + iters - 1) / iters;
+  }
+  return dim3(gx > 0 ? gx : 1, c.L);
 }
 
 template <typename T> cudaError_t launch_local_sum(const Common<T>& c, cudaStream_t st) {
@@ -440,24 +465,29 @@ template <typename T> cudaError_t launch_publish_round(const Common<T>& c, cudaS
   publish_round_kernel<T><<<1, 32, 0, st>>>(c);
   return cudaGetLastError();
 }
+// kernels that sum gradient partials: the 4-deep variant when the producer writes <= 4 partial rows per node
+#define NNDT_BY_S(S, KERNEL, ARG, C)                                                              \
+  ((S) <= 4 ? launch_pdl(KERNEL<T, 4>, grid_for(C, KERNEL<T, 4>), dim3(THREADS), 0, st, ARG)     \
+            : launch_pdl(KERNEL<T, 16>, grid_for(C, KERNEL<T, 16>), dim3(THREADS), 0, st, ARG))
 template <typename T> cudaError_t launch_dinno_update(const DinnoArgs<T>& a, cudaStream_t st) {
-  return launch_pdl(dinno_update_kernel<T>, grid_for(a.c), dim3(THREADS), 0, st, a);
+  return NNDT_BY_S(a.c.S, dinno_update_kernel, a, a.c);
 }
 template <typename T> cudaError_t launch_dsgd_mix(const Common<T>& c, cudaStream_t st) {
-  return launch_pdl(dsgd_mix_kernel<T>, grid_for(c), dim3(THREADS), 0, st, c);
+  return launch_pdl(dsgd_mix_kernel<T>, grid_for(c, dsgd_mix_kernel<T>), dim3(THREADS), 0, st, c);
 }
 template <typename T> cudaError_t launch_dsgd_step(const Common<T>& c, cudaStream_t st) {
-  return launch_pdl(dsgd_step_kernel<T>, grid_for(c), dim3(THREADS), 0, st, c);
+  return NNDT_BY_S(c.S, dsgd_step_kernel, c, c);
 }
 template <typename T> cudaError_t launch_dsgt_init(const DsgtArgs<T>& a, cudaStream_t st) {
-  return launch_pdl(dsgt_init_kernel<T>, grid_for(a.c), dim3(THREADS), 0, st, a);
+  return NNDT_BY_S(a.c.S, dsgt_init_kernel, a, a.c);
 }
 template <typename T> cudaError_t launch_dsgt_mix(const DsgtArgs<T>& a, cudaStream_t st) {
-  return launch_pdl(dsgt_mix_kernel<T>, grid_for(a.c), dim3(THREADS), 0, st, a);
+  return launch_pdl(dsgt_mix_kernel<T>, grid_for(a.c, dsgt_mix_kernel<T>), dim3(THREADS), 0, st, a);
 }
 template <typename T> cudaError_t launch_dsgt_track(const DsgtArgs<T>& a, cudaStream_t st) {
-  return launch_pdl(dsgt_track_kernel<T>, grid_for(a.c), dim3(THREADS), 0, st, a);
+  return NNDT_BY_S(a.c.S, dsgt_track_kernel, a, a.c);
 }
+#undef NNDT_BY_S
 
 #define NNDT_INST(T)                                                                  \
   template cudaError_t launch_local_sum<T>(const Common<T>&, cudaStream_t);           \

@@ -191,11 +191,12 @@ NNDT_DEVINL void wait_all_sums(const Common<T>& c, int k) {
   }
 }
 
-template <typename T>
+template <int U, typename T>
 NNDT_DEVINL Pack<T> sum_partials(const Common<T>& c, int l, int i) {
-  // all (up to 16) partial loads are issued before the first add: one L2 round trip instead of S dependent ones;
-  // the summation order stays s = 0, 1, 2, ...
-  constexpr int N = Vec<T>::N, U = 16;
+  // all (up to U) partial loads are issued before the first add: one L2 round trip instead of S dependent ones;
+  // the summation order stays s = 0, 1, 2, ...  (U = 4 for the cluster kernels' <= 4 partial rows per node: the
+  // 16-deep variant costs 48 more registers and halves the occupancy of the update kernels)
+  constexpr int N = Vec<T>::N;
   const T* gp = c.grad_part + (size_t)l * c.S * c.n_pad + i;
   Pack<T> q[U];
 #pragma unroll

@@ -197,10 +197,13 @@ class ConsensusEngine:
         d["pub_L"] = self.Lpub
         # multi-GPU: the "round published" flags can be written by publish_round_kernel on a forked graph branch
         # (round_program.py) instead of the round's last kernel.
-        # Measured (2 GPUs): the fork breaks the PDL edge into the next round's first kernel, which costs the
-        # resident 64-round graphs 2.9 us / round, while the host-fed graphs (already forked per round for the
-        # staging kernel) gain 1.9 us / round -> "auto" enables it only there.
-        sp = opt.conf.get("separate_publish", pr.conf.get("separate_publish", "auto"))
+        # Off by default.  The one-CTA publish kernel becomes ready together with the next round's forward/backward
+        # kernel, whose PDL-launched update kernel fills every remaining register file with CTAs that spin on the
+        # peers' flags: with the fp64 cluster kernel nothing is left for the publish CTA until the forward/backward
+        # CTAs exit, i.e. every rank announces its round ~34 us late (scripts/timeline_rounds.py, 2 GPUs: flag wait
+        # 33.9 us vs 2.5 us with the announcement inside the round's last kernel).  (In round 1 the fork gained
+        # 1.9 us / round on the host-fed fp32 graphs and cost 2.9 us on the resident ones.)
+        sp = opt.conf.get("separate_publish", pr.conf.get("separate_publish", False))
         if os.environ.get("NNDT_SEPARATE_PUBLISH") in ("0", "1"):       # A/B switch
             sp = os.environ["NNDT_SEPARATE_PUBLISH"] == "1"
         if sp == "auto":
