@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(THREADS) dinno_update_kernel(const DinnoArgs<T
   const T rho = cf.rho;
   const bool first = a.step == 0, last = a.step == a.pits - 1;
   tl_stamp(c, ri.k, a.step, 0);
-  if (first) { if (c.sum_mode) wait_all_sums(c, ri.k); else wait_neighbors(c, ri.gid, l, ri.k); }
+  if (first) begin_round(c, ri.gid, l, ri.k);
   tl_stamp(c, ri.k, a.step, 1);
 
   const bool fresh = first && !a.persistent;  // Adam moments restart every round (reference Q3)
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(THREADS) dsgd_mix_kernel(const Common<T> c) {
   const int l = node_of_block(c);
   const RoundInfo<T> ri = round_info(c);
   const int deg = c.deg[ri.gid * c.L + l];
-  if (c.sum_mode) wait_all_sums(c, ri.k); else wait_neighbors(c, ri.gid, l, ri.k);
+  begin_round(c, ri.gid, l, ri.k);
   const T ws = c.self_w[ri.gid * c.L + l];
   const T* w = c.nbr_w + (size_t)(ri.gid * c.L + l) * c.dmax;
   const size_t row = (size_t)l * c.n_pad;
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(THREADS) dsgt_mix_kernel(const DsgtArgs<T> a) 
   const int l = node_of_block(c);
   const RoundInfo<T> ri = round_info(c);
   const int deg = c.deg[ri.gid * c.L + l];
-  if (c.sum_mode) wait_all_sums(c, ri.k); else wait_neighbors(c, ri.gid, l, ri.k);
+  begin_round(c, ri.gid, l, ri.k);
   const T alpha = c.alpha[ri.k];
   const T ws = c.self_w[ri.gid * c.L + l];
   const T* w = c.nbr_w + (size_t)(ri.gid * c.L + l) * c.dmax;

@@ -59,7 +59,8 @@ struct Common {
   // neighbor read verifies it (nullptr = off)
   int* pub_seq;               // [2 parity, pub_L] local tags, written with the published rows
   const int64_t* nbr_seq;     // [G, L, dmax, 2] device addresses of the neighbors' tags per parity
-  int flags_in_kernel;        // 1: the round's last kernel announces it to the peers itself; 0: publish_round_kernel does
+  int flags_in_kernel;        // who tells the peers that a round is published: 2 = the first consensus kernel of the round that
+                              // reads it (default), 1 = the last kernel of the round that wrote it, 0 = publish_round_kernel
   // complete-graph ("sum") mode: Metropolis weights are uniform 1/N, so every aggregate is a function of
   // S = sum over ALL nodes.  Each rank reduces its local rows into `sum_local` and the consumers fetch the
   // network-wide sum either with one NVLS in-switch reduction (multimem.ld_reduce over `sum_mc`) or, on a

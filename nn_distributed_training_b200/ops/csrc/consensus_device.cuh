@@ -122,12 +122,23 @@ NNDT_DEVINL void announce_round(const Common<T>& c, int kn) {
   }
 }
 
+// First consensus kernel of round k (the one that reads neighbor rows).  flags_in_kernel == 2: block (0, 0) announces
+// "round k published" HERE instead of the last block of round k - 1's final kernel: that kernel wrote the rows, it is
+// complete and flushed by the time any block of this one runs (every kernel passes griddepcontrol.wait before it lets its
+// dependents launch), and the system fence + NVLink flag stores (3-4 us when they sit at the end of a kernel the next
+// forward/backward waits for) now overlap the forward/backward kernel this launch runs under.
+template <typename T>
+NNDT_DEVINL void begin_round(const Common<T>& c, int gid, int l, int k) {
+  if (c.world > 1 && c.flags_in_kernel == 2 && blockIdx.x == 0 && blockIdx.y == 0) announce_round(c, k);
+  if (c.sum_mode) wait_all_sums(c, k); else wait_neighbors(c, gid, l, k);
+}
+
 // last block of the launch: advance the round counter and announce the new round to peers
 template <typename T>
 NNDT_DEVINL void finish_round(const Common<T>& c, int k) {
   // flags_in_kernel == 0: a separate publish_round_kernel on a forked graph branch announces the round to the
   // peers (system fence + remote flag stores off the local critical path); this kernel only advances the counter.
-  const bool announce = c.world > 1 && c.flags_in_kernel;
+  const bool announce = c.world > 1 && c.flags_in_kernel == 1;
   __shared__ bool is_last;
   __syncthreads();
   if (threadIdx.x == 0) {

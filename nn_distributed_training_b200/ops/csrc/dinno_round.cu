@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(NT, 1) dinno_round_kernel(const RoundArgs ra) 
 
     // ---- consensus update of this CTA's slice of the row ----------------------------------------------------
     const bool first = p == 0, last = p == pits - 1;
-    if (first) { if (c.sum_mode) wait_all_sums(c, ri.k); else wait_neighbors(c, ri.gid, l, ri.k); }
+    if (first) begin_round(c, ri.gid, l, ri.k);
     const DinnoCoef<float> cf = dinno_coef(ra.d, ri.k, p, deg);
     const bool fresh = first && !ra.d.persistent;
     for (int v = v0 + tid; v < v1; v += NT) {

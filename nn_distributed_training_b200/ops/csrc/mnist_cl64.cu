@@ -450,20 +450,50 @@ mnist_cl64_train_kernel(const Args a, const GenericShape gs) {
       }
   }
   __syncthreads();
-  // ---- conv grads, one channel at a time: each pooled cell routes da1 to its argmax conv position; the per-thread sums
-  //      are folded over lane pairs and transposed through the dead A / dH tiles ([26][256] doubles) -----------------------------
-  double* scratch = sm.a;
-  static_assert(sizeof(double) * 26 * (NT / 2) <= sizeof(double) * (64 * WS + 64 * HS), "conv-grad scratch fits A + dH");
-#pragma unroll 1
-  for (int ch = 0; ch < F; ++ch) {
-    double cacc[26];
+  // ---- conv grads.  da1 is sparse (ReLU mask): (1) deterministic per-channel compaction of the non-zero (sample, cell)
+  //      entries (ballot + prefix over 32-entry chunks, so the order — and the fp64 sums — never depend on timing);
+  //      (2) five warps per channel walk that channel's dense list, each entry routes da1 to its argmax conv position;
+  //      (3) ONE fold over lane pairs + transposition through the dead A / dH tiles for all three channels --------------
+  constexpr int NI = MS * CELLS, NCH = NI / 32, CGW = 5, CGT = CGW * 32;     // entries / chunks per channel; warps / threads per channel
+  static_assert(F * CGW <= NT / 32 && NI % 32 == 0 && NI <= 2048, "conv-grad work split");
+  unsigned short* list = reinterpret_cast<unsigned short*>(sm.hpart);      // [F][NI] (hpart is dead: group 1's partial was consumed)
+  int* ccount = reinterpret_cast<int*>(list + F * NI);                     // [F * NCH] chunk counts, then [F] totals
+  static_assert(sizeof(unsigned short) * F * NI + sizeof(int) * (F * NCH + F) <= sizeof(double) * 64 * HS, "lists fit hpart");
+  for (int q = warp; q < F * NCH; q += NT / 32) {
+    const int ch = q / NCH, it = (q - ch * NCH) * 32 + lane;
+    const int s = it / CELLS, cell = it - s * CELLS;
+    const unsigned b = __ballot_sync(0xffffffffu, da1[s * KC + ch * CELLS + cell] != 0.0);
+    if (lane == 0) ccount[q] = __popc(b);
+  }
+  __syncthreads();
+  for (int q = warp; q < F * NCH; q += NT / 32) {
+    const int ch = q / NCH, qq = q - ch * NCH, it = qq * 32 + lane;
+    const int s = it / CELLS, cell = it - s * CELLS;
+    int pre = 0;
+    for (int j = lane; j < qq; j += 32) pre += ccount[ch * NCH + j];
 #pragma unroll
-    for (int i = 0; i < 26; ++i) cacc[i] = 0.0;
-    for (int it = tid; it < MS * CELLS; it += NT) {
-      const int s = it / CELLS, cell = it - s * CELLS;
-      const double g = da1[s * KC + ch * CELLS + cell];
-      if (g != 0.0) {
-        const int ai = sm.arg[s * KC + ch * CELLS + cell] & 3;
+    for (int o = 16; o > 0; o >>= 1) pre += __shfl_xor_sync(0xffffffffu, pre, o);
+    const bool nz = da1[s * KC + ch * CELLS + cell] != 0.0;
+    const unsigned b = __ballot_sync(0xffffffffu, nz);
+    if (nz) list[ch * NI + pre + __popc(b & ((1u << lane) - 1u))] =
+        (unsigned short)(it | ((sm.arg[s * KC + ch * CELLS + cell] & 3) << 11));
+    if (qq == NCH - 1 && lane == 0) ccount[F * NCH + ch] = pre + __popc(b);
+  }
+  __syncthreads();
+  double* scratch = sm.a;                                                   // [F * 26][CGT / 2]
+  static_assert(sizeof(double) * F * 26 * (CGT / 2) <= sizeof(double) * (64 * WS + 64 * HS), "conv-grad scratch fits A + dH");
+  {
+    const int gch = warp / CGW, tl = tid - gch * CGT;
+    if (gch < F) {
+      double cacc[26];
+#pragma unroll
+      for (int i = 0; i < 26; ++i) cacc[i] = 0.0;
+      const int n = ccount[F * NCH + gch];
+      for (int j = tl; j < n; j += CGT) {
+        const unsigned e = list[gch * NI + j];
+        const int it = e & 2047, ai = e >> 11;
+        const int s = it / CELLS, cell = it - s * CELLS;
+        const double g = da1[s * KC + gch * CELLS + cell];
         const int pr = cell / PHW, px = cell - pr * PHW;
         const PT* src = img + s * 224 + (2 * pr + (ai >> 1)) * HW + 2 * px + (ai & 1);
 #pragma unroll
@@ -472,22 +502,21 @@ mnist_cl64_train_kernel(const Args a, const GenericShape gs) {
           for (int kx = 0; kx < KS; ++kx) cacc[ky * 5 + kx] += g * pix(src[ky * HW + kx]);
         cacc[25] += g;
       }
-    }
 #pragma unroll
-    for (int i = 0; i < 26; ++i) {
-      const double v = cacc[i] + __shfl_xor_sync(0xffffffffu, cacc[i], 1);
-      if ((lane & 1) == 0) scratch[i * (NT / 2) + (tid >> 1)] = v;
+      for (int i = 0; i < 26; ++i) {
+        const double v = cacc[i] + __shfl_xor_sync(0xffffffffu, cacc[i], 1);
+        if ((lane & 1) == 0) scratch[(gch * 26 + i) * (CGT / 2) + (tl >> 1)] = v;
+      }
     }
-    __syncthreads();
-    for (int o = warp; o < 26; o += NT / 32) {
-      double v = 0.0;
-#pragma unroll
-      for (int q = 0; q < NT / 64; ++q) v += scratch[o * (NT / 2) + lane + 32 * q];
-      v = wsum(v);
-      // this CTA's share goes straight into rank 0's collection buffer (its h_loc rows, dead since barrier #2)
-      if (lane == 0) st_dsmem(map_to(sm.h_loc + c * 80 + (o < 25 ? ch * 25 + o : 75 + ch), 0u), v);
-    }
-    __syncthreads();
+  }
+  __syncthreads();
+  for (int o = warp; o < F * 26; o += NT / 32) {
+    double v = 0.0;
+    for (int q = lane; q < CGT / 2; q += 32) v += scratch[o * (CGT / 2) + q];
+    v = wsum(v);
+    const int ch = o / 26, i = o - ch * 26;
+    // this CTA's share goes straight into rank 0's collection buffer (its h_loc rows, dead since barrier #2)
+    if (lane == 0) st_dsmem(map_to(sm.h_loc + c * 80 + (i < 25 ? ch * 25 + i : 75 + ch), 0u), v);
   }
   stamp(prof, 12, tid);
   cluster_sync();                                        // #3: all six conv-gradient shares are in rank 0's buffer

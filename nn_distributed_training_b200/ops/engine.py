@@ -209,7 +209,13 @@ class ConsensusEngine:
         if sp == "auto":
             sp = forked_graphs
         self.separate_publish = bool(ctx.world_size > 1 and sp)
-        d["flags_in_kernel"] = 0 if self.separate_publish else 1
+        # in-kernel announcement: "start" = by the first consensus kernel of the round that READS the rows (its block 0,
+        # under the forward/backward kernel), "end" = by the last kernel of the round that wrote them (3-4 us of system
+        # fence + NVLink stores on the critical path of every round)
+        self.announce = os.environ.get("NNDT_ANNOUNCE", str(opt.conf.get("announce", pr.conf.get("announce", "start"))))
+        if self.announce not in ("start", "end"):
+            raise ValueError(f"announce must be 'start' or 'end', got {self.announce!r}")
+        d["flags_in_kernel"] = 0 if self.separate_publish else (2 if self.announce == "start" else 1)
         if pr.fused is not None and getattr(pr, "track_tloss", False) and self.dtype == torch.float32:
             # the kernel that consumes a gradient also folds that step's loss into the EMA tracker
             d.update(loss_part=pr.fused.loss_part.data_ptr(), tloss=pr.tloss_local.data_ptr(),

@@ -29,12 +29,13 @@ CONFS = {
 METRICS = ["forward_pass_count", "validation_loss", "consensus_error", "top1_accuracy", "current_epoch"]
 
 
-def build(ctx, N, graph, conf, backend, M=200, pipeline="resident"):
+def build(ctx, N, graph, conf, backend, M=200, pipeline="resident", separate_publish=False):
     data = synthetic_mnist(M * N, seed=3)
     val = synthetic_mnist(128, seed=4)
     shards = [data.select(torch.arange(i * M, (i + 1) * M)) for i in range(N)]
     pconf = {"problem_name": "t", "train_batch_size": 32, "val_batch_size": 64, "metrics": METRICS,
-             "metrics_config": {"evaluate_frequency": 3}, "optimizer_config": conf, "input_pipeline": pipeline}
+             "metrics_config": {"evaluate_frequency": 3}, "optimizer_config": conf, "input_pipeline": pipeline,
+             "separate_publish": separate_publish}
     torch.manual_seed(5)
     base = MNISTConvNet(3, 5, 64)
     return DistMNISTProblem(graph, base, torch.nn.NLLLoss(), shards, val, ctx.device, pconf, ctx=ctx,
@@ -103,6 +104,7 @@ def main():
     ap.add_argument("--nodes", type=int, default=6)
     ap.add_argument("--graph", default="cycle")
     ap.add_argument("--pipeline", default="resident")   # host: device-initiated staging + forked peer announcement
+    ap.add_argument("--separate-publish", type=int, default=0)   # 1: peers announced by publish_round_kernel on a forked branch
     ap.add_argument("--delayed", type=int, default=0)   # 1: time-varying graphs (link drops) + a deliberately slow rank
     args = ap.parse_args()
     ctx = DistContext.from_env(use_cuda=bool(args.cuda))
@@ -113,7 +115,7 @@ def main():
         return delayed(ctx, N, G, backend)
     ok = True
     for alg, conf in CONFS.items():
-        pr = build(ctx, N, G, conf, backend, pipeline=args.pipeline)
+        pr = build(ctx, N, G, conf, backend, pipeline=args.pipeline, separate_publish=bool(args.separate_publish))
         opt = build_optimizer(pr, ctx.device, copy.deepcopy(conf))
         opt.train()
         theta = pr.gather_rows(pr.arena.theta).cpu()

@@ -34,10 +34,11 @@ def test_nccl_peer_mapped_ranks_match_single_process(graph, pipeline):
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     nproc = min(8, n)         # every GPU of the box: 2 on the development boxes, 8 on the scaling box
-    r = _launch(nproc, ["--cuda", "1", "--nodes", str(3 * nproc), "--graph", graph, "--pipeline", pipeline], 29612)
+    forked = pipeline == "host"           # also cover the optional forked announcement (default: inside the round's last kernel)
+    r = _launch(nproc, ["--cuda", "1", "--nodes", str(3 * nproc), "--graph", graph, "--pipeline", pipeline,
+                        "--separate-publish", str(int(forked))], 29612)
     assert "DIST_RESULT PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
-    if pipeline in ("host", "auto"):      # auto = staged-resident multi-round graphs for DiNNO / DSGD
-        assert "separate_publish=True" in r.stdout
+    assert f"separate_publish={forked}" in r.stdout
 
 
 @pytest.mark.gpu
