@@ -77,7 +77,11 @@ if __name__ == "__main__":
     launches("launches_f64")
     summarize("mnist_tc", "mnist_tc_train_kernel<32> — tcgen05 / TMEM / TMA conv-net forward+backward, 10 nodes x 2 clusters x 6 CTAs (120 CTAs)",
               "Algorithmic bytes per launch: parameters 10 x 111 KB (W1 slices are TMA-loaded exactly once per cluster: 2 x 111 KB per node), one "
-              "640 x 784 B batch, gradient rows 20 x 111 KB written once.")
+              "640 x 784 B batch, gradient rows 20 x 111 KB written once = 2.8 MB read, 2.2 MB written.  Measured (same report, `--page raw`): "
+              "`l1tex__m_xbar2l1tex_read_bytes.sum` 6.83 MB of which 2.43 MB are DSMEM reads of the cluster reduce-scatter / dH gather "
+              "(`..._mem_dshared`) and 2.95 MB are the W1 tensor-map TMA loads (`..._mem_global_op_tma_ld`: 3 boxes of 32 x 64 floats per CTA "
+              "for 24 needed columns, 1.33x over-fetch) -> 4.40 MB from L2 = 1.57x algorithmic; `l1tex2xbar_write_bytes` 6.74 MB of which "
+              "2.43 MB DSMEM -> 4.31 MB to L2 = 1.9x algorithmic (gradient rows + per-CTA losses + phase stamps).  DRAM: 1.85 MB read, 0 written.")
     summarize("mnist_cl64", "mnist_cl64_train_kernel<32> — float64 K-split cluster conv-net forward+backward (fp64 CUDA cores), 120 CTAs", "")
     summarize("mnist_train", "mnist_kernel<5,768,train> — fused MNIST conv-net forward+backward, 10 nodes x 13 batch slices (130 CTAs)", "")
     summarize("mnist_eval", "mnist_kernel<8,768,eval> — forward-only validation pass", "")
