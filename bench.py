@@ -453,7 +453,9 @@ def run_ours(args):
                         "timing": "W warm-up rounds; graphs of the K timed rounds captured beforehand; device rank barrier + host gate; "
                                   "CUDA events, max over ranks",
                         "l2": f"inputs {NODES_PER_GPU * SAMPLES_PER_NODE * 784 / 1e6:.0f} MB/GPU > L2: every round's rows are gathered at "
-                              f"random from the HBM-resident shards (never re-used within {SAMPLES_PER_NODE // BATCH} steps); no flush"},
+                              f"random from the HBM-resident shards (never re-used within {SAMPLES_PER_NODE // BATCH} steps); no flush",
+                        "host_placement": (f"rank bound to the {ctx.local_cpus} CPUs NVML reports local to its GPU (pinned staging buffers on that socket)"
+                                           if getattr(ctx, "local_cpus", None) else "process affinity unchanged")},
             "extra": extra,
         }
         print(json.dumps(out))

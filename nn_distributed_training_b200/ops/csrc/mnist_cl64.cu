@@ -199,10 +199,22 @@ mnist_cl64_train_kernel(const Args a, const GenericShape gs) {
     const int pr = cell / PHW, px = cell - pr * PHW;
     const PT* src = img + s * 224 + (2 * pr) * HW + 2 * px;
     double patch[6][6];
+    if constexpr (kDoublePix) {
+      // a patch row is six consecutive doubles starting at the even column 2 px: three 16-byte loads, and consecutive lanes
+      // (consecutive px) read consecutive 16-byte chunks -> half the shared-memory wavefronts of 8-byte loads at stride 2
 #pragma unroll
-    for (int r = 0; r < 6; ++r)
+      for (int r = 0; r < 6; ++r)
 #pragma unroll
-      for (int q = 0; q < 6; ++q) patch[r][q] = pix(src[r * HW + q]);
+        for (int q = 0; q < 6; q += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(src + r * HW + q);
+          patch[r][q] = v.x; patch[r][q + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int q = 0; q < 6; ++q) patch[r][q] = pix(src[r * HW + q]);
+    }
     const bool ok = sm.valid[s] != 0.f;
 #pragma unroll 1
     for (int ch = 0; ch < F; ++ch) {

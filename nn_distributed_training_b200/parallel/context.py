@@ -23,6 +23,40 @@ def block_partition(n_items: int, n_parts: int) -> List[int]:
     return [base + (1 if r < rem else 0) for r in range(n_parts)]
 
 
+def cpus_from_mask(words: Sequence[int], bits_per_word: int = 64) -> set:
+    """CPU indices of an NVML affinity bitmask (array of machine words, CPU ``64 w + b`` = bit ``b`` of word ``w``)."""
+    return {w * bits_per_word + b for w, word in enumerate(words) for b in range(bits_per_word) if (int(word) >> b) & 1}
+
+
+def bind_to_local_cpus(device_index: int, min_cpus: int = 4, nvml=None) -> Optional[set]:
+    """NUMA placement for the host-fed input pipeline: restrict this process to the CPUs NVML reports as local to its GPU
+    *before* any pinned host buffer is allocated, so first-touch places the staging dataset on the GPU's own socket — with
+    8 ranks on a two-socket node, device-initiated pulls from the far socket cross the inter-socket link and share it.
+    Returns the CPU set applied, or None when nothing was changed: NVML missing, ``NNDT_NUMA_BIND=0``, the mask does not
+    narrow the current affinity, or the cgroup leaves fewer than ``min_cpus`` of the local CPUs."""
+    if os.environ.get("NNDT_NUMA_BIND", "1") == "0" or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        if nvml is None:
+            import pynvml as nvml
+            nvml.nvmlInit()
+        handle = None
+        try:        # CUDA_VISIBLE_DEVICES may renumber the devices: match by UUID
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            handle = nvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:  # noqa: BLE001
+            handle = nvml.nvmlDeviceGetHandleByIndex(device_index)
+        allowed = set(os.sched_getaffinity(0))
+        n_words = (max(allowed) // 64) + 1 if allowed else 1
+        local = cpus_from_mask(nvml.nvmlDeviceGetCpuAffinity(handle, n_words)) & allowed
+        if len(local) < min_cpus or local == allowed:
+            return None
+        os.sched_setaffinity(0, local)
+        return local
+    except Exception:  # noqa: BLE001  (placement is an optimisation, never a failure)
+        return None
+
+
 class DistContext:
     """Rank/world info plus the collectives the non-fused paths need."""
 
@@ -32,6 +66,7 @@ class DistContext:
         self.world_size = int(world_size)
         self.device = torch.device(device)
         self.group = group
+        self.local_cpus = None
 
     # -- construction --------------------------------------------------
     @classmethod
@@ -48,13 +83,16 @@ class DistContext:
         device = torch.device("cuda", local_rank) if cuda else torch.device("cpu")
         if cuda:
             torch.cuda.set_device(device)
+            bound = bind_to_local_cpus(local_rank)
         if world > 1 and not dist.is_initialized():
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             os.environ.setdefault("MASTER_PORT", "29500")
             be = backend or ("nccl" if cuda else "gloo")
             kw = {"device_id": device} if (cuda and be == "nccl") else {}
             dist.init_process_group(be, rank=rank, world_size=world, **kw)
-        return cls(rank, world, device)
+        ctx = cls(rank, world, device)
+        ctx.local_cpus = None if not cuda or not bound else len(bound)      # CPUs this rank was bound to (NUMA-local to its GPU)
+        return ctx
 
     @property
     def is_distributed(self) -> bool:

@@ -269,3 +269,39 @@ def test_choose_spb_fills_one_wave():
             assert 4 <= spb <= SPB
             if spb > 4:                          # a smaller value would not have fitted
                 assert L * -(-B // (spb - 1)) > 148
+
+
+def test_numa_binding_helper_is_safe_without_nvml(monkeypatch):
+    """parallel/context.py: bind_to_local_cpus never raises and only ever narrows the affinity to NVML's local CPUs."""
+    import os
+    from nn_distributed_training_b200.parallel import context as C
+    assert C.cpus_from_mask([0b1011, 0b1]) == {0, 1, 3, 64}
+    before = os.sched_getaffinity(0)
+    monkeypatch.setenv("NNDT_NUMA_BIND", "0")
+    assert C.bind_to_local_cpus(0) is None
+
+    class FakeNvml:            # a GPU whose local CPUs are the first half of the allowed set
+        def __init__(self, cpus): self.cpus = cpus
+        def nvmlDeviceGetHandleByUUID(self, u): raise RuntimeError("no uuid")
+        def nvmlDeviceGetHandleByIndex(self, i): return i
+        def nvmlDeviceGetCpuAffinity(self, h, n):
+            words = [0] * n
+            for c in self.cpus:
+                words[c // 64] |= 1 << (c % 64)
+            return words
+
+    monkeypatch.setenv("NNDT_NUMA_BIND", "1")
+    allowed = sorted(before)
+    half = set(allowed[: max(1, len(allowed) // 2)])
+    got = C.bind_to_local_cpus(0, min_cpus=1, nvml=FakeNvml(half))
+    try:
+        if len(allowed) >= 2:
+            assert got == half and os.sched_getaffinity(0) == half
+        else:
+            assert got is None
+        # a mask that would leave too few CPUs is ignored
+        os.sched_setaffinity(0, before)
+        assert C.bind_to_local_cpus(0, min_cpus=len(allowed) + 1, nvml=FakeNvml(half)) is None
+        assert os.sched_getaffinity(0) == before
+    finally:
+        os.sched_setaffinity(0, before)
