@@ -16,9 +16,10 @@ region in both arms.
 
 Precision.  The reference runs float64 end to end (experiments/dist_mnist_ex.py:19), so the
 headline of BOTH arms is float64 (``--dtype fp64``, the default): ours = the hand-written fp64
-forward/backward kernel (csrc/mnist_generic.cu) + the fp64 instantiation of the fused consensus
-kernels.  ``extra.fp32`` carries the same measurement at float32 for both arms (ours = the fp32
-tensor-core kernels; reference = the same stock classes under torch.set_default_dtype(float32)).
+cluster kernel (csrc/mnist_cl64.cu: K-split over 6-CTA clusters, fp64 CUDA cores, DSMEM reductions)
++ the fp64 instantiation of the fused consensus kernels.  ``extra.fp32`` carries the same measurement
+at float32 for both arms (ours = csrc/mnist_tc.cu, tcgen05 / TMEM / tensor-map TMA with 3xTF32;
+reference = the same stock classes under torch.set_default_dtype(float32)).
 
 * ``value``  — device-timed (CUDA events on the launching stream, max over ranks), shards
   resident in HBM (the framework's native pipeline); each GPU's shard set is sized > L2 and
